@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+# -*- coding: utf-8 -*-
+"""bench.py -- lasso sweeps/s on B200 (BASELINE.json metric) with roofline and CPU baseline.
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path
+
+A "step" is one sweep: BLOCK block steps, each reading the column block A_m for the block
+gradient A_m^T r and again for A_m D (prox, line search, error and updates fused).  The
+workload is BASELINE.json configs[1]: dense fp32 lasso 10,000 x 100,000, 100 column
+blocks, synthetic Gaussian A with unit-l2 rows (reference recipe parameters.py:20-33),
+generated on the device.  A (4 GB) is far larger than L2 (126 MB), so nothing is flushed
+between timed steps.
+
+`value`  : sweeps/s with everything resident in HBM (K fused launches, CUDA events).
+`e2e`    : sweeps/s through the reference-facing API, ClassLasso.run(): host b -> device,
+           the solve, x -> host, all inside the timed region (A is uploaded once by
+           GPU_Calculation(A, BLOCK), exactly as in the reference driver cpu_vs_gpu.py:131).
+`roofline`: algorithmic bytes of a sweep / kernel time vs the
+           measured HBM copy peak of MEASURED_PEAKS.json.
+`cpu_baseline`: the oracle port of the reference's CPU path on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "lasso_sweeps_per_s"
+UNIT = "sweeps/s"
+# BASELINE.json configs[1]
+C2 = dict(N=10000, K=100000, BLOCK=100, den=0.01, seed=2, dtype="float")
+FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def sweep_bytes(N, K, BLOCK, s):
+    return 2 * N * K * s + 5 * BLOCK * N * s + 4 * K * s
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(layout):
+    """dram bytes per sweep from the committed ncu --set full capture, if any"""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(layout)
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2] or [r for (_, r) in self.rows]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ data
+def make_device_instance(torch, device, N, K, BLOCK, den, seed, torch_dtype, ld, layout="row"):
+    """reference recipe (parameters.py:20-33) on the device: Gaussian A, unit-l2 rows,
+    sparse x_true, b = A x_true + e, mu = 0.1 |A^T b|_inf.  Returns (store, b, mu)."""
+    w = K // BLOCK
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    rows = N if layout == "row" else w
+    store = torch.zeros((BLOCK, rows, ld), dtype=torch_dtype, device=device)
+    sq = torch.zeros(N, dtype=torch.float64, device=device)
+    for m in range(BLOCK):
+        blk = torch.randn((N, w), generator=gen, dtype=torch_dtype, device=device)
+        sq += (blk.double() ** 2).sum(dim=1)
+        if layout == "row":
+            store[m, :, :w] = blk
+        else:
+            store[m, :, :N] = blk.t()
+    inv = (1.0 / sq.sqrt()).to(torch_dtype)
+    x_true = torch.randn(K, generator=gen, dtype=torch.float64, device=device)
+    x_true *= (torch.rand(K, generator=gen, dtype=torch.float64, device=device) < den)
+    b = torch.zeros(N, dtype=torch.float64, device=device)
+    for m in range(BLOCK):
+        if layout == "row":
+            store[m, :, :w] *= inv[:, None]
+            b += store[m, :, :w].double() @ x_true[m * w:(m + 1) * w]
+        else:
+            store[m, :, :N] *= inv[None, :]
+            b += store[m, :, :N].double().t() @ x_true[m * w:(m + 1) * w]
+    b += 1e-2 * torch.randn(N, generator=gen, dtype=torch.float64, device=device)
+    gmax = 0.0
+    for m in range(BLOCK):
+        if layout == "row":
+            g = store[m, :, :w].double().t() @ b
+        else:
+            g = store[m, :, :N].double() @ b
+        gmax = max(gmax, float(g.abs().max()))
+    return store, b.cpu().numpy().reshape(-1, 1), 0.1 * gmax
+
+
+# ------------------------------------------------------------------------------ CPU arm
+def cpu_sample(threads_note=True):
+    """the oracle port (NumPy/BLAS, all host threads) on a bounded C2-shaped sample:
+    10,000 x 10,000 fp64, 10 blocks of w=1000 (1/10 of C2's columns)."""
+    from oracle import lasso_oracle as orc
+    N, K, BLOCK = 10000, 10000, 10
+    rng = np.random.RandomState(2)
+    A = rng.standard_normal((N, K))
+    A /= np.linalg.norm(A, axis=1, keepdims=True)
+    xt = rng.standard_normal((K, 1)) * (rng.rand(K, 1) < 0.01)
+    b = A @ xt + 1e-2 * rng.standard_normal((N, 1))
+    mu = 0.1 * np.max(np.abs(A.T @ b))
+    return orc, A, b, mu, N, K, BLOCK
+
+
+def run_cpu(orc, A, b, mu, BLOCK, sweeps):
+    t0 = time.time()
+    o = orc.lasso_oracle(A, b, mu, BLOCK, BLOCK * sweeps, None, faithful=False)
+    dt = time.time() - t0
+    assert o["iters"] == BLOCK * sweeps
+    return dt
+
+
+def cpu_baseline_block(sweeps=6):
+    orc, A, b, mu, N, K, BLOCK = cpu_sample()
+    run_cpu(orc, A, b, mu, BLOCK, 1)
+    dt = run_cpu(orc, A, b, mu, BLOCK, sweeps)
+    frac = K / C2["K"]
+    sample_sweeps_per_s = sweeps / dt
+    return {"value": sample_sweeps_per_s * frac, "unit": UNIT, "cores": os.cpu_count(),
+            "kind": "port",
+            "sample": "oracle port (NumPy fp64, BLAS threads) on 10000x10000, 10 blocks of w=1000 "
+                      "(1/10 of the C2 columns), %d sweeps in %.2f s = %.2f sample-sweeps/s; value is "
+                      "scaled by bytes (x%.2f) to the full 10000x100000 sweep" % (sweeps, dt, sample_sweeps_per_s, frac)}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    orc, A, b, mu, N, K, BLOCK = cpu_sample()
+    for _ in range(max(args.warmup, 1)):
+        run_cpu(orc, A, b, mu, BLOCK, 1)
+    t0 = time.time()
+    for _ in range(args.steps):
+        run_cpu(orc, A, b, mu, BLOCK, 1)
+    dt = time.time() - t0
+    frac = K / C2["K"]
+    value = args.steps / dt * frac
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps / frac * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "dense lasso 10000x100000, 100 column blocks (C2); each step = one sweep "
+                               "of a 10000x10000 / 10-block sample, scaled by bytes"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                         "sample": "one sweep of a 10000x10000, 10-block fp64 sample per step; NumPy/BLAS "
+                                   "with all host threads; scaled x%.2f by bytes to C2" % frac},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def main_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from convex_optimization_b200 import _lib, lasso
+    from convex_optimization_b200.gpu_calculation import GPU_Calculation
+    import ctypes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+
+    cfg = dict(C2)
+    if args.small:
+        cfg.update(N=2000, K=20000, BLOCK=20)
+    N, K, BLOCK = cfg["N"], cfg["K"], cfg["BLOCK"]
+    s = 4 if cfg["dtype"] == "float" else 8
+    layout = args.layout
+
+    class Cal(GPU_Calculation):
+        TYPE = cfg["dtype"]
+        LAYOUT = layout
+        DEVICE = local_rank
+    ld = Cal.padded_ld(N, K, BLOCK)
+    tdt = torch.float32 if cfg["dtype"] == "float" else torch.float64
+    store, b, mu = make_device_instance(torch, device, N, K, BLOCK, cfg["den"], cfg["seed"] + rank,
+                                        tdt, ld, layout)
+    cal = Cal.from_device_blocks(store, N, K, BLOCK)
+    if args.slot_bytes or args.keep_tiles >= 0:
+        cal.set_tuning(args.slot_bytes, args.keep_tiles)
+    lib, ctx = cal._lib, cal.ctx
+    d_ATA = cal.diag_ATA
+    geo = cal.run_config()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    # ---- value: K sweeps, resident, device-timed ------------------------------------
+    bb = np.ascontiguousarray(b.reshape(-1))
+    _lib.check(lib.b200l_set_problem(ctx, _lib.dptr(bb)))
+
+    def sweep():
+        _lib.check(lib.b200l_run(ctx, None, BLOCK, float(mu), -1.0, None, None, None, None, None))
+
+    for _ in range(args.warmup):
+        sweep()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        sweep()
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * 1e3 / ms_per_step
+
+    # kernel-only time of the dominant kernel (one launch = one sweep), events inside the lib
+    kms = ctypes.c_double()
+    ktimes = []
+    for _ in range(min(args.steps, 10)):
+        _lib.check(lib.b200l_run(ctx, None, BLOCK, float(mu), -1.0, None, None, None, None,
+                                 ctypes.byref(kms)))
+        ktimes.append(kms.value)
+    kernel_ms = float(np.mean(ktimes))
+    obj = ctypes.c_double()
+    _lib.check(lib.b200l_objective(ctx, float(mu), ctypes.byref(obj)))
+
+    # ---- e2e: through ClassLasso.run(), host b in, host x out -------------------------
+    e2e_sweeps = args.e2e_sweeps
+    solver = lasso.ClassLasso(cal, d_ATA, store, b, mu, BLOCK, BLOCK * e2e_sweeps)
+    for _ in range(2):
+        solver.run(SILENCE=True)
+    barrier()
+    t0 = time.time()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        solver.run(SILENCE=True)
+    barrier()
+    e2e_dt = time.time() - t0
+    if world > 1:
+        t = torch.tensor([e2e_dt], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    e2e_value = world * e2e_steps * e2e_sweeps / e2e_dt
+    nnz = int(np.count_nonzero(solver.x))
+
+    if rank == 0:
+        W = sweep_bytes(N, K, BLOCK, s)
+        peak, peak_src = measured_peak()
+        achieved = W / (kernel_ms * 1e-3) / 1e9
+        traffic = ncu_traffic(layout)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if s == 4 else "f64",
+            "data": "synthetic",
+            "config": {"workload": "dense %s lasso %dx%d, %d column blocks, %s A layout; 1 step = 1 sweep; "
+                                   "A=%.1f GB >> L2 so no flush between steps%s"
+                                   % ("fp32" if s == 4 else "fp64", N, K, BLOCK, layout,
+                                      N * K * s / 1e9,
+                                      "; one independent instance per GPU (replicas)" if world > 1 else ""),
+                       "launch": geo, "objective_after_bench": obj.value},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "lasso_fused_rowmajor", "kernel_ms_per_launch": kernel_ms,
+                         "algorithmic_bytes_per_launch": W, "peak_source": peak_src,
+                         "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "single_pass_GBs": (W - N * K * s) / (kernel_ms * 1e-3) / 1e9},
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(N * 8 + 4 * BLOCK * e2e_sweeps),
+                    "d2h_bytes_per_step": int(K * 8 + 24),
+                    "sweeps_per_call": e2e_sweeps, "calls": e2e_steps, "nnz_x": nnz,
+                    "api": "ClassLasso.run() (host b -> device, fused solve, x -> host)"},
+            "gpu_launches": args.steps,
+            "clocks": clocks,
+        }
+        if not args.no_cpu and world == 1:
+            line["cpu_baseline"] = cpu_baseline_block()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layout", default="row", choices=["row", "transposed"])
+    ap.add_argument("--small", action="store_true", help="2000x20000 debug size (not a bench value)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--e2e-sweeps", type=int, default=5)
+    ap.add_argument("--slot-bytes", type=int, default=0)
+    ap.add_argument("--keep-tiles", type=int, default=-1)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

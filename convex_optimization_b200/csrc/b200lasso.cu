@@ -1,0 +1,1294 @@
+// b200lasso.cu -- libb200lasso.so: sm_100a implementation of the lasso block
+// proximal-gradient hot path (C ABI declared in include/b200lasso.h).
+//
+// Reference being replaced (kingold5/convex_optimization, file:line under the
+// reference tree):
+//   * iteration              lasso.py:102-157 (CPU), :228-278 (GPU mat-vecs), :508-599 (cuBLAS)
+//   * A_m^T r  / A_m d       gpu_calculation.py:20-55 / :58-91 (hand kernels), lasso.py:350-353
+//   * diag(A^T A)            gpu_calculation.py:116-137, cpu_calculation.py:35-42
+//   * prox / error           cpu_calculation.py:5-20
+//
+// Design: one persistent cooperative kernel runs whole solves.  Each CTA
+// owns a fixed slab of rows of A for every column block, so its slice of the residual r
+// and of q = A_m D never leaves shared memory.  A producer warp streams the slab tile by
+// tile with TMA bulk copies (cp.async.bulk -> UBLKCP) into an mbarrier ring; 16 consumer
+// warps use each tile for the block gradient (pass 1) and for A_m D (pass 2).  Only the
+// partial block gradients (w values per CTA), the step D (w values) and four scalars per
+// CTA cross CTAs, through L2, with two grid barriers per block step.  The step size of
+// block t is resolved lazily at the first barrier of block t+1
+// (g_{t+1} = A^T r + gamma A^T q), which removes the third barrier.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "b200lasso.h"
+
+// ------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------
+static thread_local char g_err[768] = "";
+
+static int fail(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+
+#define CK(call)                                                                   \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess)                                                     \
+            return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                        __FILE__, __LINE__);                                       \
+    } while (0)
+
+// ------------------------------------------------------------------------------------
+// constants / small device helpers
+// ------------------------------------------------------------------------------------
+constexpr int NW = 16;                 // consumer warps
+constexpr int NTC = NW * 32;           // consumer threads
+constexpr int NTHREADS = NTC + 32;     // + one producer warp
+constexpr int MAX_CS = 64;             // max stage-2 slice width (columns per CTA)
+
+template <typename T> struct VT;
+template <> struct VT<float> { using type = float4; static constexpr int V = 4; };
+template <> struct VT<double> { using type = double2; static constexpr int V = 2; };
+
+__device__ __forceinline__ float vdot(const float4 a, const float4 b) {
+    return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+}
+__device__ __forceinline__ double vdot(const double2 a, const double2 b) {
+    return a.x * b.x + a.y * b.y;
+}
+__device__ __forceinline__ void vfma(float (&acc)[4], const float4 v, const float s) {
+    acc[0] += v.x * s; acc[1] += v.y * s; acc[2] += v.z * s; acc[3] += v.w * s;
+}
+__device__ __forceinline__ void vfma(double (&acc)[2], const double2 v, const double s) {
+    acc[0] += v.x * s; acc[1] += v.y * s;
+}
+__device__ __forceinline__ float4 vpack(const float (&a)[4]) { return make_float4(a[0], a[1], a[2], a[3]); }
+__device__ __forceinline__ double2 vpack(const double (&a)[2]) { return make_double2(a[0], a[1]); }
+__device__ __forceinline__ float4 vadd(const float4 a, const float4 b) {
+    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ double2 vadd(const double2 a, const double2 b) {
+    return make_double2(a.x + b.x, a.y + b.y);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                             uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void cbar() {  // barrier over the consumer threads only
+    asm volatile("bar.sync 1, %0;" ::"n"(NTC) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// grid-wide barrier over the consumer threads of all (co-resident) CTAs
+__device__ __forceinline__ void grid_sync(unsigned long long *bar, unsigned long long &target,
+                                          int G, int tid) {
+    cbar();
+    if (tid == 0) {
+        target += (unsigned long long)G;
+        __threadfence();
+        atomicAdd(bar, 1ULL);
+        while (ld_acquire_u64(bar) < target) {
+        }
+    }
+    cbar();
+}
+
+// ------------------------------------------------------------------------------------
+// fused kernel parameters
+// ------------------------------------------------------------------------------------
+struct Ctl {
+    double rq, qq, l1, err;
+    unsigned long long kc, k_issued;
+    int stop;
+    int pad;
+};
+
+struct RunParams {
+    const void *A;
+    int64_t N;
+    int64_t blk_stride;  // elements between consecutive blocks
+    int32_t w, ld, nblocks;
+    double *x;           // [nblocks][ld]
+    const double *d;     // [nblocks][ld]
+    const double *drec;  // [nblocks][ld]
+    double *r;           // [N]
+    void *gpart;         // [G][2][ld] of T
+    double *spart;       // [G][4]
+    double *dglob;       // [ld]
+    unsigned long long *bar;
+    const int32_t *order;
+    int64_t nsteps, step0;
+    double mu, err_bound;
+    int32_t bounded;
+    double *err_hist;
+    unsigned long long *time_hist;
+    long long *state;     // [0] steps_done [1] stopped [2] block_cnt
+    double *gamma_state;  // [0] last gamma
+    // geometry
+    int32_t TR, S, slot_bytes, cs, npg, wpr, nrg, ncg, rows_max, keep;
+    // shared-memory offsets
+    int32_t off_bar, off_ctl, off_rloc, off_qloc, off_rT, off_qT, off_delta, off_redT, off_red64,
+        off_small, off_qpart;
+};
+
+// ------------------------------------------------------------------------------------
+// the fused persistent kernel, row-major blocks (nblocks, N, ld)
+// ------------------------------------------------------------------------------------
+template <typename T, int CPT>
+__global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunParams p) {
+    using VecT = typename VT<T>::type;
+    constexpr int V = VT<T>::V;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *ring = smem;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + p.off_bar);
+    uint64_t *empty = full + p.S;
+    Ctl *ctl = reinterpret_cast<Ctl *>(smem + p.off_ctl);
+    double *r_loc = reinterpret_cast<double *>(smem + p.off_rloc);
+    double *q_loc = reinterpret_cast<double *>(smem + p.off_qloc);
+    T *rT = reinterpret_cast<T *>(smem + p.off_rT);
+    T *qT = reinterpret_cast<T *>(smem + p.off_qT);
+    T *delta_s = reinterpret_cast<T *>(smem + p.off_delta);
+    T *redT = reinterpret_cast<T *>(smem + p.off_redT);
+    double *red64 = reinterpret_cast<double *>(smem + p.off_red64);
+    double *l1s = reinterpret_cast<double *>(smem + p.off_small);
+    double *es = l1s + MAX_CS;
+    double *qpart = reinterpret_cast<double *>(smem + p.off_qpart);
+
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int c = blockIdx.x, G = gridDim.x;
+    const int64_t base = p.N / G;
+    const int rem = (int)(p.N % G);
+    const int rows_c = (int)base + (c < rem ? 1 : 0);
+    const int64_t row0 = (int64_t)c * base + (c < rem ? c : rem);
+    const int TR = p.TR, S = p.S, ld = p.ld, ncg = p.ncg;
+    const int nt = (rows_c + TR - 1) / TR;
+    const T *Aall = reinterpret_cast<const T *>(p.A);
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, NW);
+        }
+        ctl->stop = 0;
+        ctl->kc = 0;
+        ctl->k_issued = 0;
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (wid == NW) {
+        // ============================ producer warp ================================
+        if (lane == 0) {
+            unsigned long long k = 0;
+            volatile int *stopf = &ctl->stop;
+            bool live = true;
+            for (int64_t step = 0; step < p.nsteps && live; ++step) {
+                const int m = p.order ? p.order[step] : (int)((p.step0 + step) % p.nblocks);
+                const T *Ab = Aall + (int64_t)m * p.blk_stride + row0 * (int64_t)ld;
+                for (int pass = 0; pass < 2 && live; ++pass) {
+                    for (int t = 0; t < nt; ++t) {
+                        const int slot = (int)(k % (unsigned)S);
+                        const uint32_t ph = (uint32_t)(((k / (unsigned)S) & 1ULL) ^ 1ULL);
+                        while (!mbar_try_wait(empty + slot, ph)) {
+                            if (*stopf) { live = false; break; }
+                        }
+                        if (!live) break;
+                        const int rows_t = min(TR, rows_c - t * TR);
+                        const uint32_t bytes = (uint32_t)rows_t * (uint32_t)ld * (uint32_t)sizeof(T);
+                        mbar_expect_tx(full + slot, bytes);
+                        tma_bulk_g2s(ring + (size_t)slot * p.slot_bytes, Ab + (int64_t)t * TR * ld,
+                                     bytes, full + slot);
+                        ++k;
+                    }
+                }
+            }
+            ctl->k_issued = k;
+        }
+        __syncwarp();
+    } else {
+        // ============================ consumer warps ===============================
+        for (int i = tid; i < rows_c; i += NTC) {
+            const double rv = p.r[row0 + i];
+            r_loc[i] = rv;
+            rT[i] = (T)rv;
+            q_loc[i] = 0.0;
+            qT[i] = (T)0;
+        }
+        cbar();
+
+        unsigned long long bar_target = 0;
+        unsigned long long kc = 0;
+        bool have_prev = false;
+        int m_prev = 0;
+        int64_t step_prev = -1;
+        double sp_rq = 0, sp_qq = 0, sp_l1 = 0, sp_err = 0;  // thread 0 only
+        double dprev = 0, xprev = 0;                          // tid < cs
+        int64_t prev_idx = -1;
+        long long block_cnt = p.state[2];
+        double gamma_last = p.gamma_state[0];
+        int stopped = 0;
+        int64_t steps_done = 0;
+        const unsigned long long t_start = globaltimer_ns();
+        const int cs = p.cs, npg = p.npg, wpr = p.wpr, nrg = p.nrg;
+        const double mu = p.mu;
+        T *gp = reinterpret_cast<T *>(p.gpart);
+
+        int cg0, rg;
+        bool p1_active;
+        if (CPT == 1) {
+            p1_active = tid < nrg * ncg;
+            cg0 = tid % ncg;
+            rg = tid / ncg;
+        } else {
+            p1_active = true;
+            cg0 = tid;
+            rg = 0;
+        }
+
+        // resolves the pending step: reduces the per-CTA scalars, applies the stop rule,
+        // computes gamma.  Returns false when the stop rule fired.
+        auto resolve_prev = [&](double &gamma_out) -> bool {
+            if (wid == 0) {
+                double a = 0, b = 0, l = 0, e = 0;
+                for (int pp = lane; pp < G; pp += 32) {
+                    a += __ldcg(p.spart + 4 * pp + 0);
+                    b += __ldcg(p.spart + 4 * pp + 1);
+                    l += __ldcg(p.spart + 4 * pp + 2);
+                    e = fmax(e, __ldcg(p.spart + 4 * pp + 3));
+                }
+                a = warp_sum(a); b = warp_sum(b); l = warp_sum(l); e = warp_max(e);
+                if (lane == 0) { ctl->rq = a; ctl->qq = b; ctl->l1 = l; ctl->err = e; }
+            }
+            cbar();
+            const double rq = ctl->rq, qq = ctl->qq, l1 = ctl->l1, err = ctl->err;
+            if (c == 0 && tid == 0 && p.err_hist) p.err_hist[step_prev] = err;
+            if (p.bounded) {                                   // lasso.py:141-150
+                if (err < p.err_bound) ++block_cnt;
+                if (m_prev == p.nblocks - 1) {
+                    if (block_cnt == p.nblocks) return false;
+                    block_cnt = 0;
+                }
+            }
+            if (qq != 0.0)                                     // lasso.py:133-136
+                gamma_last = fmin(fmax(-(rq + mu * l1) / qq, 0.0), 1.0);
+            gamma_out = gamma_last;
+            return true;
+        };
+
+        for (int64_t step = 0; step < p.nsteps; ++step) {
+            const int m = p.order ? p.order[step] : (int)((p.step0 + step) % p.nblocks);
+            steps_done = step + 1;
+
+            // -------------------- pass 1: partial (A_m^T r, A_m^T q) over the slab ----
+            T ar[CPT][V], aq[CPT][V];
+#pragma unroll
+            for (int k = 0; k < CPT; ++k)
+#pragma unroll
+                for (int e = 0; e < V; ++e) { ar[k][e] = (T)0; aq[k][e] = (T)0; }
+
+            for (int t = 0; t < nt; ++t, ++kc) {
+                const int slot = (int)(kc % (unsigned)S);
+                mbar_wait(full + slot, (uint32_t)((kc / (unsigned)S) & 1ULL));
+                const T *tile = reinterpret_cast<const T *>(ring + (size_t)slot * p.slot_bytes);
+                const int rows_t = min(TR, rows_c - t * TR);
+                const T *rTt = rT + t * TR;
+                const T *qTt = qT + t * TR;
+                if (p1_active) {
+#pragma unroll 4
+                    for (int rr = rg; rr < rows_t; rr += nrg) {
+                        const T rv = rTt[rr], qv = qTt[rr];
+                        const T *trow = tile + (size_t)rr * ld;
+#pragma unroll
+                        for (int k = 0; k < CPT; ++k) {
+                            const int cg = cg0 + k * NTC;
+                            if (CPT == 1 || cg < ncg) {
+                                const VecT v = *reinterpret_cast<const VecT *>(trow + cg * V);
+                                vfma(ar[k], v, rv);
+                                vfma(aq[k], v, qv);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + slot);
+            }
+            // combine the row groups of this CTA, publish the partial gradient
+            T *gpc = gp + (size_t)c * 2 * ld;
+            if (nrg > 1) {
+                if (p1_active) {
+                    *reinterpret_cast<VecT *>(redT + (size_t)(rg * 2 + 0) * ld + cg0 * V) = vpack(ar[0]);
+                    *reinterpret_cast<VecT *>(redT + (size_t)(rg * 2 + 1) * ld + cg0 * V) = vpack(aq[0]);
+                }
+                cbar();
+                for (int cg = tid; cg < ncg; cg += NTC) {
+                    VecT sr = *reinterpret_cast<const VecT *>(redT + cg * V);
+                    VecT sq = *reinterpret_cast<const VecT *>(redT + (size_t)ld + cg * V);
+                    for (int g2 = 1; g2 < nrg; ++g2) {
+                        sr = vadd(sr, *reinterpret_cast<const VecT *>(redT + (size_t)(g2 * 2 + 0) * ld + cg * V));
+                        sq = vadd(sq, *reinterpret_cast<const VecT *>(redT + (size_t)(g2 * 2 + 1) * ld + cg * V));
+                    }
+                    __stcg(reinterpret_cast<VecT *>(gpc + cg * V), sr);
+                    __stcg(reinterpret_cast<VecT *>(gpc + ld + cg * V), sq);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) {
+                    const int cg = cg0 + k * NTC;
+                    if (p1_active && cg < ncg) {
+                        __stcg(reinterpret_cast<VecT *>(gpc + cg * V), vpack(ar[k]));
+                        __stcg(reinterpret_cast<VecT *>(gpc + ld + cg * V), vpack(aq[k]));
+                    }
+                }
+            }
+            if (tid == 0) {
+                __stcg(p.spart + 4 * c + 0, sp_rq);
+                __stcg(p.spart + 4 * c + 1, sp_qq);
+                __stcg(p.spart + 4 * c + 2, sp_l1);
+                __stcg(p.spart + 4 * c + 3, sp_err);
+            }
+            grid_sync(p.bar, bar_target, G, tid);  // ---- B1
+
+            // -------------------- resolve the previous step (lazy gamma) -------------
+            double gamma_prev = 0.0;
+            if (have_prev) {
+                if (!resolve_prev(gamma_prev)) {
+                    stopped = 1;
+                    steps_done = step_prev + 1;
+                    break;
+                }
+                for (int i = tid; i < rows_c; i += NTC) {
+                    const double rn = r_loc[i] + gamma_prev * q_loc[i];   // lasso.py:155
+                    r_loc[i] = rn;
+                    rT[i] = (T)rn;
+                }
+            }
+
+            // -------------------- stage 2: reduce my column slice, prox ----------------
+            const int j0 = c * cs;
+            if (tid < npg * cs) {
+                const int jl = tid % cs, pg = tid / cs, j = j0 + jl;
+                double sr = 0.0, sq = 0.0;
+                if (j < ld) {
+                    for (int pp = pg; pp < G; pp += npg) {
+                        sr += (double)__ldcg(gp + ((size_t)pp * 2 + 0) * ld + j);
+                        sq += (double)__ldcg(gp + ((size_t)pp * 2 + 1) * ld + j);
+                    }
+                }
+                red64[pg * cs + jl] = sr;
+                red64[NTC + pg * cs + jl] = sq;
+            }
+            cbar();
+            if (tid < cs) {
+                double my_l1 = 0.0, my_err = 0.0;
+                if (have_prev && prev_idx >= 0)
+                    __stcg(p.x + prev_idx, xprev + gamma_prev * dprev);      // lasso.py:153
+                prev_idx = -1;
+                const int j = j0 + tid;
+                if (j < ld) {
+                    double delta = 0.0;
+                    if (j < p.w) {
+                        double gr = 0.0, gq = 0.0;
+                        for (int pg = 0; pg < npg; ++pg) {
+                            gr += red64[pg * cs + tid];
+                            gq += red64[NTC + pg * cs + tid];
+                        }
+                        const double g = gr + gamma_prev * gq;
+                        const int64_t idx = (int64_t)m * ld + j;
+                        const double xj = __ldcg(p.x + idx);
+                        const double dj = p.d[idx];
+                        if (dj > 0.0) {
+                            const double u = dj * xj - g;                     // lasso.py:114
+                            const double au = fabs(u) - mu;                   // cpu_calculation.py:5-6
+                            const double soft = au > 0.0 ? copysign(au, u) : 0.0;
+                            const double Bx = p.drec[idx] * soft;             // lasso.py:117
+                            delta = Bx - xj;                                  // lasso.py:119
+                            my_l1 = fabs(Bx) - fabs(xj);
+                            const double gx = g - xj;                         // cpu_calculation.py:15-20
+                            const double proj = fmin(fmax(gx, -mu), mu);
+                            my_err = fabs(g - proj);
+                            dprev = delta;
+                            xprev = xj;
+                            prev_idx = idx;
+                        }
+                    }
+                    __stcg(p.dglob + j, delta);
+                }
+                l1s[tid] = my_l1;
+                es[tid] = my_err;
+            }
+            cbar();
+            if (tid == 0) {
+                double a = 0.0, e = 0.0;
+                for (int i = 0; i < cs; ++i) { a += l1s[i]; e = fmax(e, es[i]); }
+                sp_l1 = a;
+                sp_err = e;
+            }
+            grid_sync(p.bar, bar_target, G, tid);  // ---- B2
+
+            for (int j = tid; j < ld; j += NTC) delta_s[j] = (T)__ldcg(p.dglob + j);
+            cbar();
+
+            // -------------------- pass 2: q = A_m D over the slab ----------------------
+            for (int t = 0; t < nt; ++t, ++kc) {
+                const int slot = (int)(kc % (unsigned)S);
+                mbar_wait(full + slot, (uint32_t)((kc / (unsigned)S) & 1ULL));
+                const T *tile = reinterpret_cast<const T *>(ring + (size_t)slot * p.slot_bytes);
+                const int rows_t = min(TR, rows_c - t * TR);
+                const int part = (wpr > 1) ? (wid % wpr) : 0;
+                const int rr0 = (wpr > 1) ? (wid / wpr) : wid;
+                const int rstep = (wpr > 1) ? TR : NW;
+                const int cstride = 32 * wpr;
+                for (int rr = rr0; rr < rows_t; rr += rstep) {
+                    const T *trow = tile + (size_t)rr * ld;
+                    T a0 = (T)0, a1 = (T)0;
+                    int cg = lane + 32 * part;
+                    for (; cg + cstride < ncg; cg += 2 * cstride) {
+                        const VecT v0 = *reinterpret_cast<const VecT *>(trow + cg * V);
+                        const VecT d0 = *reinterpret_cast<const VecT *>(delta_s + cg * V);
+                        const VecT v1 = *reinterpret_cast<const VecT *>(trow + (cg + cstride) * V);
+                        const VecT d1 = *reinterpret_cast<const VecT *>(delta_s + (cg + cstride) * V);
+                        a0 += vdot(v0, d0);
+                        a1 += vdot(v1, d1);
+                    }
+                    if (cg < ncg) {
+                        const VecT v0 = *reinterpret_cast<const VecT *>(trow + cg * V);
+                        const VecT d0 = *reinterpret_cast<const VecT *>(delta_s + cg * V);
+                        a0 += vdot(v0, d0);
+                    }
+                    const T qv = warp_sum(a0 + a1);
+                    if (lane == 0) qpart[(size_t)(t * TR + rr) * wpr + part] = (double)qv;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + slot);
+            }
+            cbar();
+            {
+                double trq = 0.0, tqq = 0.0;
+                for (int i = tid; i < rows_c; i += NTC) {
+                    double q = 0.0;
+                    for (int pt = 0; pt < wpr; ++pt) q += qpart[(size_t)i * wpr + pt];
+                    q_loc[i] = q;
+                    qT[i] = (T)q;
+                    trq += r_loc[i] * q;                                     // lasso.py:129
+                    tqq += q * q;                                            // lasso.py:132
+                }
+                trq = warp_sum(trq);
+                tqq = warp_sum(tqq);
+                if (lane == 0) { red64[wid] = trq; red64[NW + wid] = tqq; }
+                cbar();
+                if (tid == 0) {
+                    double a = 0.0, b = 0.0;
+                    for (int i = 0; i < NW; ++i) { a += red64[i]; b += red64[NW + i]; }
+                    sp_rq = a;
+                    sp_qq = b;
+                }
+            }
+            have_prev = true;
+            m_prev = m;
+            step_prev = step;
+            if (c == 0 && tid == 0 && p.time_hist) p.time_hist[step] = globaltimer_ns() - t_start;
+        }
+
+        // -------------------- resolve the last step ----------------------------------
+        if (!stopped && have_prev) {
+            if (tid == 0) {
+                __stcg(p.spart + 4 * c + 0, sp_rq);
+                __stcg(p.spart + 4 * c + 1, sp_qq);
+                __stcg(p.spart + 4 * c + 2, sp_l1);
+                __stcg(p.spart + 4 * c + 3, sp_err);
+            }
+            grid_sync(p.bar, bar_target, G, tid);
+            double gamma_prev = 0.0;
+            if (!resolve_prev(gamma_prev)) {
+                stopped = 1;
+            } else {
+                for (int i = tid; i < rows_c; i += NTC) r_loc[i] += gamma_prev * q_loc[i];
+                if (tid < cs && prev_idx >= 0) __stcg(p.x + prev_idx, xprev + gamma_prev * dprev);
+            }
+        }
+        cbar();
+        for (int i = tid; i < rows_c; i += NTC) p.r[row0 + i] = r_loc[i];
+        if (c == 0 && tid == 0) {
+            p.state[0] = steps_done;
+            p.state[1] = stopped;
+            p.state[2] = block_cnt;
+            p.gamma_state[0] = gamma_last;
+        }
+        if (tid == 0) {
+            ctl->kc = kc;
+            *(volatile int *)&ctl->stop = 1;
+        }
+    }
+    __syncthreads();
+    // drain TMA copies the producer issued past the stop point
+    if (tid == 0) {
+        for (unsigned long long k = ctl->kc; k < ctl->k_issued; ++k)
+            mbar_wait(full + (int)(k % (unsigned)S), (uint32_t)((k / (unsigned)S) & 1ULL));
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------
+// plain (non-persistent) kernels: weighted column sums, row dots, reductions
+// ------------------------------------------------------------------------------------
+// part[chunk][col] = sum_{rows in chunk} A[row][col] * (SQ ? A[row][col] : vec[row])
+template <typename T, bool SQ>
+__global__ void __launch_bounds__(256) colwsum_partial(const T *__restrict__ A, int64_t M, int ncols,
+                                                       int64_t ld, const double *__restrict__ vec,
+                                                       double *__restrict__ part, int rows_per_chunk) {
+    using VecT = typename VT<T>::type;
+    constexpr int V = VT<T>::V;
+    const int chunk = blockIdx.x;
+    const int64_t r0 = (int64_t)chunk * rows_per_chunk;
+    const int64_t r1 = min(M, r0 + rows_per_chunk);
+    const int ncg = ncols / V;  // ncols is a multiple of V (padded)
+    for (int cg = threadIdx.x; cg < ncg; cg += blockDim.x) {
+        double acc[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] = 0.0;
+#pragma unroll 4
+        for (int64_t r = r0; r < r1; ++r) {
+            const VecT v = __ldg(reinterpret_cast<const VecT *>(A + r * ld + (int64_t)cg * V));
+            const T *ve = reinterpret_cast<const T *>(&v);
+            if (SQ) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) acc[e] += (double)ve[e] * (double)ve[e];
+            } else {
+                const double s = vec[r];
+#pragma unroll
+                for (int e = 0; e < V; ++e) acc[e] += (double)ve[e] * s;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) part[(int64_t)chunk * ncols + cg * V + e] = acc[e];
+    }
+}
+
+// out[col] (+)= sum_chunk part[chunk][col]   (fixed order: deterministic)
+__global__ void reduce_partials(const double *__restrict__ part, int nchunks, int ncols,
+                                double *__restrict__ out, int accumulate) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncols) return;
+    double s = 0.0;
+    for (int ch = 0; ch < nchunks; ++ch) s += part[(int64_t)ch * ncols + col];
+    out[col] = accumulate ? out[col] + s : s;
+}
+
+// out[row] (+)= sum_col A[row][col] * (SQ ? A[row][col] : vec[col]); one warp per row
+template <typename T, bool SQ>
+__global__ void __launch_bounds__(256) rowdot_kernel(const T *__restrict__ A, int64_t M, int ncols,
+                                                     int64_t ld, const double *__restrict__ vec,
+                                                     double *__restrict__ out, int accumulate) {
+    using VecT = typename VT<T>::type;
+    constexpr int V = VT<T>::V;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int ncg = ncols / V;
+    for (int64_t r = warp; r < M; r += nwarps) {
+        double acc = 0.0;
+        for (int cg = lane; cg < ncg; cg += 32) {
+            const VecT v = __ldg(reinterpret_cast<const VecT *>(A + r * ld + (int64_t)cg * V));
+            const T *ve = reinterpret_cast<const T *>(&v);
+#pragma unroll
+            for (int e = 0; e < V; ++e)
+                acc += (double)ve[e] * (SQ ? (double)ve[e] : vec[cg * V + e]);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) out[r] = accumulate ? out[r] + acc : acc;
+    }
+}
+
+__global__ void finish_diag(const double *__restrict__ dsum, double *__restrict__ d,
+                            double *__restrict__ drec, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = dsum[i];
+    d[i] = v;
+    drec[i] = v > 0.0 ? 1.0 / v : 0.0;   // lasso.py:29-30
+}
+
+__global__ void neg_copy(const double *__restrict__ b, double *__restrict__ r, int64_t n, double sign) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) r[i] = sign * b[i];
+}
+
+// single-CTA deterministic objective: 0.5*|r|^2 + mu*|x|_1
+__global__ void __launch_bounds__(1024) objective_kernel(const double *__restrict__ r, int64_t n,
+                                                         const double *__restrict__ x, int64_t nx,
+                                                         double mu, double *out) {
+    __shared__ double s1[32], s2[32];
+    double a = 0.0, b = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) a += r[i] * r[i];
+    for (int64_t i = threadIdx.x; i < nx; i += blockDim.x) b += fabs(x[i]);
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = a; s2[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double A2 = 0.0, B2 = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { A2 += s1[i]; B2 += s2[i]; }
+        out[0] = 0.5 * A2 + mu * B2;
+        out[1] = A2;
+        out[2] = B2;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------
+struct b200l_ctx {
+    int dtype, layout, device;
+    int64_t N, K;
+    int32_t nblocks, w;
+    int64_t ld;        // padded leading dimension of a device block row
+    int64_t brows;     // rows of a device block (N row-major, w transposed)
+    int64_t xld;       // stride of x/d per block
+    size_t esize;
+    cudaStream_t stream;
+    const void *A;
+    int sm_count, smem_optin;
+    // solver state
+    double *x, *d, *drec, *r, *b, *dsum;
+    // scratch
+    double *vin, *vout, *part;
+    int part_chunks;
+    void *gpart;
+    double *spart, *dglob, *gamma_state, *err_hist, *objbuf;
+    unsigned long long *bar, *time_hist;
+    long long *state;
+    int32_t *order;
+    int64_t hist_cap, order_cap;
+    int64_t step_counter;
+    int have_problem;
+    cudaEvent_t ev0, ev1;
+    // tuning
+    int32_t slot_target, keep_tiles;
+    // cached geometry
+    RunParams geo;
+    int grid, smem_bytes, cpt, nt_max;
+    int geo_valid;
+};
+
+static int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+extern "C" const char *b200l_last_error(void) { return g_err; }
+extern "C" int b200l_abi_version(void) { return B200L_ABI_VERSION; }
+
+extern "C" int b200l_device_count(int *count) {
+    if (!count) return fail("count is NULL");
+    int n = 0;
+    CK(cudaGetDeviceCount(&n));
+    if (n <= 0) return fail("no CUDA device present (this library has no CPU fallback)");
+    *count = n;
+    return 0;
+}
+
+extern "C" int b200l_device_info(int device, char *name, int name_len, int *sm_count,
+                                 int *smem_optin, int *l2_bytes) {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (name && name_len > 0) {
+        strncpy(name, prop.name, (size_t)name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (smem_optin) *smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (l2_bytes) *l2_bytes = prop.l2CacheSize;
+    return 0;
+}
+
+extern "C" int b200l_ctx_create(b200l_ctx **out, int dtype, int layout, int64_t N, int64_t K,
+                                int32_t nblocks, int device) {
+    if (!out) return fail("out is NULL");
+    *out = nullptr;
+    if (dtype != B200L_F32 && dtype != B200L_F64) return fail("dtype must be B200L_F32 or B200L_F64");
+    if (layout != B200L_ROWMAJOR && layout != B200L_TRANSPOSED) return fail("bad layout %d", layout);
+    if (N <= 0 || K <= 0 || nblocks <= 0) return fail("N, K, nblocks must be positive");
+    if (K % nblocks != 0)
+        return fail("K=%lld is not divisible by nblocks=%d (reference requirement, cpu_calculation.py:27)",
+                    (long long)K, nblocks);
+    int ndev = 0;
+    if (b200l_device_count(&ndev)) return 1;
+    if (device < 0 || device >= ndev) return fail("device %d out of range (have %d)", device, ndev);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail("device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+
+    b200l_ctx *c = new b200l_ctx();
+    memset(c, 0, sizeof(*c));
+    c->dtype = dtype;
+    c->layout = layout;
+    c->device = device;
+    c->N = N;
+    c->K = K;
+    c->nblocks = nblocks;
+    c->w = (int32_t)(K / nblocks);
+    c->esize = dtype == B200L_F32 ? 4 : 8;
+    const int V = (int)(16 / c->esize);
+    if (layout == B200L_ROWMAJOR) {
+        c->ld = round_up(c->w, V);
+        c->brows = N;
+        c->xld = c->ld;
+    } else {
+        c->ld = round_up(N, V);
+        c->brows = c->w;
+        c->xld = round_up(c->w, V);
+    }
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    c->slot_target = 32768;
+    c->keep_tiles = -1;
+
+    const int64_t nx = (int64_t)nblocks * c->xld;
+    const int64_t vmax = std::max<int64_t>(std::max<int64_t>(N, K), nx) + 64;
+    c->part_chunks = 4 * c->sm_count;
+    const int64_t part_cols = std::max<int64_t>(c->ld, c->xld);
+#define ALLOC(ptr, bytes) CK(cudaMalloc((void **)&(ptr), (size_t)(bytes)))
+    ALLOC(c->x, nx * 8);
+    ALLOC(c->d, nx * 8);
+    ALLOC(c->drec, nx * 8);
+    ALLOC(c->dsum, nx * 8);
+    ALLOC(c->r, N * 8);
+    ALLOC(c->b, N * 8);
+    ALLOC(c->vin, vmax * 8);
+    ALLOC(c->vout, vmax * 8);
+    ALLOC(c->part, (int64_t)c->part_chunks * part_cols * 8);
+    ALLOC(c->gpart, (int64_t)c->sm_count * 2 * c->xld * c->esize + 256);
+    ALLOC(c->spart, (int64_t)c->sm_count * 4 * 8);
+    ALLOC(c->dglob, c->xld * 8);
+    ALLOC(c->gamma_state, 8);
+    ALLOC(c->objbuf, 64);
+    ALLOC(c->bar, 64);
+    ALLOC(c->state, 64);
+#undef ALLOC
+    CK(cudaMemset(c->x, 0, nx * 8));
+    CK(cudaMemset(c->d, 0, nx * 8));
+    CK(cudaMemset(c->drec, 0, nx * 8));
+    CK(cudaMemset(c->r, 0, N * 8));
+    CK(cudaMemset(c->b, 0, N * 8));
+    CK(cudaMemset(c->gamma_state, 0, 8));
+    CK(cudaMemset(c->state, 0, 64));
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+    *out = c;
+    return 0;
+}
+
+extern "C" int b200l_ctx_destroy(b200l_ctx *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    void *ptrs[] = {c->x, c->d, c->drec, c->dsum, c->r, c->b, c->vin, c->vout, c->part, c->gpart,
+                    c->spart, c->dglob, c->gamma_state, c->objbuf, c->bar, c->state, c->err_hist,
+                    c->time_hist, c->order};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    delete c;
+    return 0;
+}
+
+extern "C" int b200l_ctx_ld(const b200l_ctx *c, int64_t *ld) {
+    if (!c || !ld) return fail("NULL argument");
+    *ld = c->ld;
+    return 0;
+}
+
+extern "C" int b200l_ctx_set_stream(b200l_ctx *c, void *stream) {
+    if (!c) return fail("ctx is NULL");
+    c->stream = (cudaStream_t)stream;
+    return 0;
+}
+
+extern "C" int b200l_ctx_bind_A(b200l_ctx *c, const void *A_dev) {
+    if (!c || !A_dev) return fail("NULL argument");
+    if (((uintptr_t)A_dev) % 128 != 0) return fail("A_dev must be 128-byte aligned");
+    cudaPointerAttributes attr;
+    CK(cudaPointerGetAttributes(&attr, A_dev));
+    if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)
+        return fail("A_dev is not a device pointer");
+    c->A = A_dev;
+    c->have_problem = 0;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// device-level mat-vecs on block m (vectors are device doubles)
+// ------------------------------------------------------------------------------------
+template <typename T>
+static int colwsum_dev(b200l_ctx *c, const T *Ablk, int64_t M, int ncols, int64_t ld, const double *vec,
+                       double *out, bool sq, int accumulate) {
+    int chunks = (int)std::min<int64_t>(c->part_chunks, M);
+    int rpc = (int)((M + chunks - 1) / chunks);
+    chunks = (int)((M + rpc - 1) / rpc);
+    if (sq)
+        colwsum_partial<T, true><<<chunks, 256, 0, c->stream>>>(Ablk, M, ncols, ld, vec, c->part, rpc);
+    else
+        colwsum_partial<T, false><<<chunks, 256, 0, c->stream>>>(Ablk, M, ncols, ld, vec, c->part, rpc);
+    reduce_partials<<<(ncols + 127) / 128, 128, 0, c->stream>>>(c->part, chunks, ncols, out, accumulate);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+static int rowdot_dev(b200l_ctx *c, const T *Ablk, int64_t M, int ncols, int64_t ld, const double *vec,
+                      double *out, bool sq, int accumulate) {
+    const int64_t warps = std::min<int64_t>(M, (int64_t)c->sm_count * 64);
+    const int blocks = (int)((warps + 7) / 8);
+    if (sq)
+        rowdot_kernel<T, true><<<blocks, 256, 0, c->stream>>>(Ablk, M, ncols, ld, vec, out, accumulate);
+    else
+        rowdot_kernel<T, false><<<blocks, 256, 0, c->stream>>>(Ablk, M, ncols, ld, vec, out, accumulate);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// g[xld] = A_m^T r[N]
+template <typename T>
+static int gemv_t_dev(b200l_ctx *c, int m, const double *r, double *g, bool sq) {
+    const T *Ablk = reinterpret_cast<const T *>(c->A) + (int64_t)m * c->brows * c->ld;
+    if (c->layout == B200L_ROWMAJOR)
+        return colwsum_dev<T>(c, Ablk, c->N, (int)c->ld, c->ld, r, g, sq, 0);
+    return rowdot_dev<T>(c, Ablk, c->w, (int)c->ld, c->ld, r, g, sq, 0);
+}
+// q[N] (+)= A_m d[xld]
+template <typename T>
+static int gemv_n_dev(b200l_ctx *c, int m, const double *dvec, double *q, int accumulate) {
+    const T *Ablk = reinterpret_cast<const T *>(c->A) + (int64_t)m * c->brows * c->ld;
+    if (c->layout == B200L_ROWMAJOR)
+        return rowdot_dev<T>(c, Ablk, c->N, (int)c->ld, c->ld, dvec, q, false, accumulate);
+    return colwsum_dev<T>(c, Ablk, c->w, (int)c->ld, c->ld, dvec, q, false, accumulate);
+}
+
+static int need_A(b200l_ctx *c) {
+    if (!c) return fail("ctx is NULL");
+    if (!c->A) return fail("no device matrix bound (call b200l_ctx_bind_A first)");
+    CK(cudaSetDevice(c->device));
+    return 0;
+}
+
+static int compute_diag(b200l_ctx *c) {
+    // the transposed layout pads N, so the row-dot must not see padding: it is zero-filled
+    for (int m = 0; m < c->nblocks; ++m) {
+        double *out = c->dsum + (int64_t)m * c->xld;
+        int rc = c->dtype == B200L_F32 ? gemv_t_dev<float>(c, m, nullptr, out, true)
+                                       : gemv_t_dev<double>(c, m, nullptr, out, true);
+        if (rc) return rc;
+    }
+    const int64_t nx = (int64_t)c->nblocks * c->xld;
+    finish_diag<<<(int)((nx + 255) / 256), 256, 0, c->stream>>>(c->dsum, c->d, c->drec, nx);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200l_diag_ata(b200l_ctx *c, double *out_host) {
+    if (need_A(c)) return 1;
+    if (!out_host) return fail("out_host is NULL");
+    if (compute_diag(c)) return 1;
+    CK(cudaMemcpy2DAsync(out_host, (size_t)c->w * 8, c->d, (size_t)c->xld * 8, (size_t)c->w * 8,
+                         (size_t)c->nblocks, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int b200l_gemv_t(b200l_ctx *c, int32_t m, const double *r_host, double *g_host) {
+    if (need_A(c)) return 1;
+    if (m < 0 || m >= c->nblocks) return fail("block index %d out of range", m);
+    if (!r_host || !g_host) return fail("NULL vector");
+    const int64_t nin = c->layout == B200L_ROWMAJOR ? c->N : c->ld;
+    CK(cudaMemsetAsync(c->vin, 0, (size_t)nin * 8, c->stream));
+    CK(cudaMemcpyAsync(c->vin, r_host, (size_t)c->N * 8, cudaMemcpyHostToDevice, c->stream));
+    int rc = c->dtype == B200L_F32 ? gemv_t_dev<float>(c, m, c->vin, c->vout, false)
+                                   : gemv_t_dev<double>(c, m, c->vin, c->vout, false);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(g_host, c->vout, (size_t)c->w * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int b200l_gemv_n(b200l_ctx *c, int32_t m, const double *d_host, double *q_host) {
+    if (need_A(c)) return 1;
+    if (m < 0 || m >= c->nblocks) return fail("block index %d out of range", m);
+    if (!d_host || !q_host) return fail("NULL vector");
+    CK(cudaMemsetAsync(c->vin, 0, (size_t)c->xld * 8, c->stream));
+    CK(cudaMemcpyAsync(c->vin, d_host, (size_t)c->w * 8, cudaMemcpyHostToDevice, c->stream));
+    int rc = c->dtype == B200L_F32 ? gemv_n_dev<float>(c, m, c->vin, c->vout, 0)
+                                   : gemv_n_dev<double>(c, m, c->vin, c->vout, 0);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(q_host, c->vout, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// solver state
+// ------------------------------------------------------------------------------------
+static int reset_state(b200l_ctx *c) {
+    const int64_t nx = (int64_t)c->nblocks * c->xld;
+    CK(cudaMemsetAsync(c->x, 0, (size_t)nx * 8, c->stream));
+    neg_copy<<<(int)((c->N + 255) / 256), 256, 0, c->stream>>>(c->b, c->r, c->N, -1.0);
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(c->state, 0, 64, c->stream));
+    CK(cudaMemsetAsync(c->gamma_state, 0, 8, c->stream));
+    c->step_counter = 0;
+    return 0;
+}
+
+extern "C" int b200l_set_problem(b200l_ctx *c, const double *b_host) {
+    if (need_A(c)) return 1;
+    if (!b_host) return fail("b_host is NULL");
+    CK(cudaMemcpyAsync(c->b, b_host, (size_t)c->N * 8, cudaMemcpyHostToDevice, c->stream));
+    if (!c->have_problem) {
+        if (compute_diag(c)) return 1;
+        c->have_problem = 1;
+    }
+    return reset_state(c);
+}
+
+extern "C" int b200l_reset(b200l_ctx *c) {
+    if (need_A(c)) return 1;
+    if (!c->have_problem) return fail("b200l_set_problem has not been called");
+    return reset_state(c);
+}
+
+extern "C" int b200l_set_x(b200l_ctx *c, const double *x_host) {
+    if (need_A(c)) return 1;
+    if (!c->have_problem) return fail("b200l_set_problem has not been called");
+    if (!x_host) return fail("x_host is NULL");
+    const int64_t nx = (int64_t)c->nblocks * c->xld;
+    CK(cudaMemsetAsync(c->x, 0, (size_t)nx * 8, c->stream));
+    CK(cudaMemcpy2DAsync(c->x, (size_t)c->xld * 8, x_host, (size_t)c->w * 8, (size_t)c->w * 8,
+                         (size_t)c->nblocks, cudaMemcpyHostToDevice, c->stream));
+    neg_copy<<<(int)((c->N + 255) / 256), 256, 0, c->stream>>>(c->b, c->r, c->N, -1.0);
+    CK(cudaGetLastError());
+    for (int m = 0; m < c->nblocks; ++m) {
+        const double *xm = c->x + (int64_t)m * c->xld;
+        int rc = c->dtype == B200L_F32 ? gemv_n_dev<float>(c, m, xm, c->r, 1)
+                                       : gemv_n_dev<double>(c, m, xm, c->r, 1);
+        if (rc) return rc;
+    }
+    CK(cudaMemsetAsync(c->state, 0, 64, c->stream));
+    c->step_counter = 0;
+    return 0;
+}
+
+extern "C" int b200l_get_x(b200l_ctx *c, double *x_host) {
+    if (!c || !x_host) return fail("NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpy2DAsync(x_host, (size_t)c->w * 8, c->x, (size_t)c->xld * 8, (size_t)c->w * 8,
+                         (size_t)c->nblocks, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int b200l_get_r(b200l_ctx *c, double *r_host) {
+    if (!c || !r_host) return fail("NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(r_host, c->r, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int b200l_objective(b200l_ctx *c, double mu, double *value) {
+    if (!c || !value) return fail("NULL argument");
+    CK(cudaSetDevice(c->device));
+    objective_kernel<<<1, 1024, 0, c->stream>>>(c->r, c->N, c->x, (int64_t)c->nblocks * c->xld, mu,
+                                                c->objbuf);
+    CK(cudaGetLastError());
+    double h[3];
+    CK(cudaMemcpyAsync(h, c->objbuf, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *value = h[0];
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// fused launch
+// ------------------------------------------------------------------------------------
+extern "C" int b200l_set_tuning(b200l_ctx *c, int32_t slot_bytes_target, int32_t keep_tiles) {
+    if (!c) return fail("ctx is NULL");
+    c->slot_target = slot_bytes_target > 0 ? slot_bytes_target : 32768;
+    c->keep_tiles = keep_tiles;
+    c->geo_valid = 0;
+    return 0;
+}
+
+typedef void (*fused_fn)(const RunParams);
+
+template <typename T>
+static fused_fn pick_kernel(int cpt) {
+    switch (cpt) {
+        case 1: return lasso_fused_rowmajor<T, 1>;
+        case 2: return lasso_fused_rowmajor<T, 2>;
+        case 4: return lasso_fused_rowmajor<T, 4>;
+        default: return nullptr;
+    }
+}
+
+static int plan_geometry(b200l_ctx *c) {
+    if (c->geo_valid) return 0;
+    if (c->layout != B200L_ROWMAJOR)
+        return fail("the fused kernel currently supports the ROWMAJOR layout only");
+    RunParams &g = c->geo;
+    memset(&g, 0, sizeof(g));
+    const int es = (int)c->esize, V = 16 / es;
+    const int ld = (int)c->ld;
+    const int64_t rowbytes = (int64_t)ld * es;
+    if (rowbytes > 32768)
+        return fail("block width w=%d needs %lld-byte rows; the fused kernel supports rows up to 32 KiB "
+                    "(use more column blocks)", c->w, (long long)rowbytes);
+    int G = c->sm_count;
+    const int rows_max = (int)((c->N + G - 1) / G);
+    const int ncg = ld / V;
+    int cpt = 1;
+    while (cpt * NTC < ncg) cpt *= 2;
+    if (cpt > 4) return fail("internal: cpt=%d", cpt);
+    const int nrg = cpt == 1 ? std::max(1, NTC / ncg) : 1;
+    int TR = 1;
+    while ((int64_t)TR * 2 * rowbytes <= c->slot_target && TR * 2 <= 64 &&
+           TR < std::max(1, rows_max))
+        TR *= 2;
+    const int wpr = TR >= NW ? 1 : NW / TR;
+    int cs = (int)round_up((ld + G - 1) / G, 32 / es);
+    if (cs > MAX_CS) return fail("internal: slice width %d > %d", cs, MAX_CS);
+    const int npg = NTC / cs;
+    const int slot_bytes = (int)round_up((int64_t)TR * rowbytes, 128);
+    const int rows_pad = (int)round_up(std::max(rows_max, 1), std::max(TR, 8));
+
+    int off = 0;
+    auto take = [&](int bytes) { int o = off; off += (int)round_up(bytes, 128); return o; };
+    // the ring goes first (offset 0); sized after the fixed part is known
+    int fixed = 0;
+    {
+        off = 0;
+        take(2 * 64 * 8);                 // barriers (up to 64 slots)
+        take((int)sizeof(Ctl));
+        take(rows_pad * 8);               // r_loc
+        take(rows_pad * 8);               // q_loc
+        take(rows_pad * es);              // rT
+        take(rows_pad * es);              // qT
+        take(ld * es);                    // delta
+        take(nrg > 1 ? nrg * 2 * ld * es : 16);   // redT
+        take(2 * NTC * 8);                // red64
+        take(2 * MAX_CS * 8);             // l1s, es
+        take(rows_pad * wpr * 8);         // qpart
+        fixed = off;
+    }
+    const int avail = c->smem_optin - fixed;
+    int S = avail / slot_bytes;
+    if (S > 64) S = 64;
+    if (S < 2)
+        return fail("shared memory too small for the fused kernel: fixed=%d slot=%d optin=%d (N/SM=%d rows, "
+                    "w=%d)", fixed, slot_bytes, c->smem_optin, rows_max, c->w);
+    const int nt_max = (rows_max + TR - 1) / TR;
+    if (S > 2 * nt_max + 2) S = 2 * nt_max + 2;   // more slots than two passes of tiles is useless
+    off = 0;
+    take(S * slot_bytes);
+    g.off_bar = take(2 * 64 * 8);
+    g.off_ctl = take((int)sizeof(Ctl));
+    g.off_rloc = take(rows_pad * 8);
+    g.off_qloc = take(rows_pad * 8);
+    g.off_rT = take(rows_pad * es);
+    g.off_qT = take(rows_pad * es);
+    g.off_delta = take(ld * es);
+    g.off_redT = take(nrg > 1 ? nrg * 2 * ld * es : 16);
+    g.off_red64 = take(2 * NTC * 8);
+    g.off_small = take(2 * MAX_CS * 8);
+    g.off_qpart = take(rows_pad * wpr * 8);
+    c->smem_bytes = off;
+    c->grid = G;
+    c->cpt = cpt;
+    c->nt_max = nt_max;
+    g.TR = TR; g.S = S; g.slot_bytes = slot_bytes; g.cs = cs; g.npg = npg; g.wpr = wpr;
+    g.nrg = nrg; g.ncg = ncg; g.rows_max = rows_max; g.keep = 0;
+
+    fused_fn fn = c->dtype == B200L_F32 ? pick_kernel<float>(cpt) : pick_kernel<double>(cpt);
+    if (!fn) return fail("internal: no kernel for cpt=%d", cpt);
+    CK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_bytes));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, NTHREADS, c->smem_bytes));
+    if (occ < 1) return fail("fused kernel does not fit on an SM (smem=%d)", c->smem_bytes);
+    int coop = 0;
+    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
+    if (!coop) return fail("device does not support cooperative launch");
+    c->geo_valid = 1;
+    return 0;
+}
+
+extern "C" int b200l_run_config(b200l_ctx *c, int32_t *grid, int32_t *threads, int32_t *smem_bytes,
+                                int32_t *tile_rows, int32_t *ring_slots, int32_t *tiles_per_slab) {
+    if (need_A(c)) return 1;
+    if (plan_geometry(c)) return 1;
+    if (grid) *grid = c->grid;
+    if (threads) *threads = NTHREADS;
+    if (smem_bytes) *smem_bytes = c->smem_bytes;
+    if (tile_rows) *tile_rows = c->geo.TR;
+    if (ring_slots) *ring_slots = c->geo.S;
+    if (tiles_per_slab) *tiles_per_slab = c->nt_max;
+    return 0;
+}
+
+extern "C" int b200l_run(b200l_ctx *c, const int32_t *order_host, int64_t nsteps, double mu,
+                         double err_bound, double *err_hist_host, double *time_hist_host,
+                         int64_t *steps_done, int32_t *stopped, double *kernel_ms) {
+    if (need_A(c)) return 1;
+    if (!c->have_problem) return fail("b200l_set_problem has not been called");
+    if (nsteps < 0) return fail("nsteps < 0");
+    if (plan_geometry(c)) return 1;
+    if (nsteps == 0) {
+        if (steps_done) *steps_done = 0;
+        if (stopped) *stopped = 0;
+        if (kernel_ms) *kernel_ms = 0.0;
+        return 0;
+    }
+    if (order_host) {
+        for (int64_t i = 0; i < nsteps; ++i)
+            if (order_host[i] < 0 || order_host[i] >= c->nblocks)
+                return fail("order[%lld]=%d out of range", (long long)i, order_host[i]);
+        if (c->order_cap < nsteps) {
+            if (c->order) CK(cudaFree(c->order));
+            CK(cudaMalloc((void **)&c->order, (size_t)nsteps * 4));
+            c->order_cap = nsteps;
+        }
+        CK(cudaMemcpyAsync(c->order, order_host, (size_t)nsteps * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    if ((err_hist_host || time_hist_host) && c->hist_cap < nsteps) {
+        if (c->err_hist) CK(cudaFree(c->err_hist));
+        if (c->time_hist) CK(cudaFree(c->time_hist));
+        CK(cudaMalloc((void **)&c->err_hist, (size_t)nsteps * 8));
+        CK(cudaMalloc((void **)&c->time_hist, (size_t)nsteps * 8));
+        c->hist_cap = nsteps;
+    }
+    if (err_hist_host) CK(cudaMemsetAsync(c->err_hist, 0, (size_t)nsteps * 8, c->stream));
+    if (time_hist_host) CK(cudaMemsetAsync(c->time_hist, 0, (size_t)nsteps * 8, c->stream));
+    CK(cudaMemsetAsync(c->bar, 0, 64, c->stream));
+
+    RunParams p = c->geo;
+    p.A = c->A;
+    p.N = c->N;
+    p.blk_stride = c->brows * c->ld;
+    p.w = c->w;
+    p.ld = (int32_t)c->ld;
+    p.nblocks = c->nblocks;
+    p.x = c->x; p.d = c->d; p.drec = c->drec; p.r = c->r;
+    p.gpart = c->gpart; p.spart = c->spart; p.dglob = c->dglob; p.bar = c->bar;
+    p.order = order_host ? c->order : nullptr;
+    p.nsteps = nsteps;
+    p.step0 = c->step_counter;
+    p.mu = mu;
+    p.err_bound = err_bound;
+    p.bounded = err_bound >= 0.0 ? 1 : 0;
+    p.err_hist = err_hist_host ? c->err_hist : nullptr;
+    p.time_hist = time_hist_host ? c->time_hist : nullptr;
+    p.state = c->state;
+    p.gamma_state = c->gamma_state;
+
+    fused_fn fn = c->dtype == B200L_F32 ? pick_kernel<float>(c->cpt) : pick_kernel<double>(c->cpt);
+    void *args[] = {(void *)&p};
+    const bool want_sync = steps_done || stopped || kernel_ms || err_hist_host || time_hist_host;
+    if (kernel_ms) CK(cudaEventRecord(c->ev0, c->stream));
+    CK(cudaLaunchCooperativeKernel((const void *)fn, dim3(c->grid), dim3(NTHREADS), args,
+                                   (size_t)c->smem_bytes, c->stream));
+    if (kernel_ms) CK(cudaEventRecord(c->ev1, c->stream));
+    c->step_counter += nsteps;
+    if (!want_sync) return 0;
+
+    long long st[3];
+    CK(cudaMemcpyAsync(st, c->state, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+    std::vector<unsigned long long> tbuf;
+    if (err_hist_host)
+        CK(cudaMemcpyAsync(err_hist_host, c->err_hist, (size_t)nsteps * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (time_hist_host) {
+        tbuf.resize((size_t)nsteps);
+        CK(cudaMemcpyAsync(tbuf.data(), c->time_hist, (size_t)nsteps * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    if (time_hist_host)
+        for (int64_t i = 0; i < nsteps; ++i) time_hist_host[i] = (double)tbuf[(size_t)i] * 1e-9;
+    if (steps_done) *steps_done = st[0];
+    if (stopped) *stopped = (int32_t)st[1];
+    if (kernel_ms) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        *kernel_ms = (double)ms;
+    }
+    return 0;
+}

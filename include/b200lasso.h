@@ -1,0 +1,130 @@
+/*
+ * b200lasso.h -- C ABI of libb200lasso.so: the B200 (sm_100a) implementation of the
+ * lasso block proximal-gradient hot path of kingold5/convex_optimization.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, int
+ * status returns (0 = ok, non-zero = failure, text via b200l_last_error()), an opaque
+ * context, no Python or torch types.  The Python mirror of the reference interface
+ * (convex_optimization_b200/{gpu_calculation,lasso}.py) binds it with ctypes; see
+ * INTEGRATION.md for the stub a maintainer of the reference would add.
+ *
+ * Every entry point names the reference interface (file:line under the reference
+ * tree) it replaces.  There is no CPU fallback: every compute entry point fails when
+ * no CUDA device is present.
+ */
+#ifndef B200LASSO_H
+#define B200LASSO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200L_ABI_VERSION 1
+
+/* arithmetic type of A and of the inner products (vectors and line-search scalars are
+ * always kept in double, SURVEY.md section 7 "keep line-search scalars in f64") */
+#define B200L_F32 0
+#define B200L_F64 1
+
+/* device layout of A.  ROWMAJOR is the reference's GPU layout (BLOCK, N, w)
+ * (gpu_calculation.py:172-173); TRANSPOSED is the pre-transposed (BLOCK, w, N) copy the
+ * reference only sketched (gpu_calculation.py:94-113,174 and README:3). */
+#define B200L_ROWMAJOR 0
+#define B200L_TRANSPOSED 1
+
+typedef struct b200l_ctx b200l_ctx;
+
+/* -- diagnostics ------------------------------------------------------------------ */
+const char *b200l_last_error(void);          /* text of the last failure on this thread */
+int b200l_abi_version(void);
+int b200l_device_count(int *count);          /* fails (non-zero) without a CUDA driver/GPU */
+/* name, SM count, max opt-in shared memory per block, L2 bytes of `device` */
+int b200l_device_info(int device, char *name, int name_len, int *sm_count,
+                      int *smem_optin, int *l2_bytes);
+
+/* -- context ----------------------------------------------------------------------
+ * Replaces GPU_Calculation.__init__/init_cpu_array/init_gpu_array
+ * (gpu_calculation.py:148-236): problem shape, block count, device buffers.
+ * N rows, K columns, nblocks column blocks of width w = K / nblocks (K % nblocks == 0,
+ * as the reference requires, cpu_calculation.py:27).  `ld` (out) is the padded leading
+ * dimension, in elements, of one row of a device block: ROWMAJOR blocks are (N, ld) with
+ * ld >= w, TRANSPOSED blocks are (w, ld) with ld >= N; rows start 16-byte aligned. */
+int b200l_ctx_create(b200l_ctx **out, int dtype, int layout, int64_t N, int64_t K,
+                     int32_t nblocks, int device);
+int b200l_ctx_destroy(b200l_ctx *ctx);
+int b200l_ctx_ld(const b200l_ctx *ctx, int64_t *ld);
+/* stream all work of this context is issued on (a cudaStream_t; NULL = default stream) */
+int b200l_ctx_set_stream(b200l_ctx *ctx, void *stream);
+/* Device storage of A, owned by the caller (a torch CUDA tensor in the Python mirror;
+ * the reference's A_b_gpu, gpu_calculation.py:224): nblocks contiguous blocks of
+ * rows*ld elements of `dtype`, padding zero-filled, pointer 128-byte aligned. */
+int b200l_ctx_bind_A(b200l_ctx *ctx, const void *A_dev);
+
+/* -- legacy mat-vec entry points (host vectors, as the reference's methods) ---------
+ * diag_ata  : column squared norms d_k, out[K] doubles, block-major
+ *             (GPU_Calculation.diag_ATA gpu_calculation.py:246-261, kernel :116-137;
+ *              cpu_calculation.py:35-42).
+ * gemv_t    : g[w] = A_m^T r[N]   (mat_tMulVec_DiffSize gpu_calculation.py:264-277,
+ *             kernel :20-55; fun_s12 cpu_calculation.py:30-31; cublasDgemv 'N' lasso.py:336).
+ * gemv_n    : q[N] = A_m d[w]     (matMulVec_DiffSize gpu_calculation.py:280-292,
+ *             kernel :58-91; fun_s22 cpu_calculation.py:45-46; cublasDgemv 'T' lasso.py:342).
+ * Vectors are host doubles; the copies are inside the call, like the reference's. */
+int b200l_diag_ata(b200l_ctx *ctx, double *out_host);
+int b200l_gemv_t(b200l_ctx *ctx, int32_t m, const double *r_host, double *g_host);
+int b200l_gemv_n(b200l_ctx *ctx, int32_t m, const double *d_host, double *q_host);
+
+/* -- fused solver state -------------------------------------------------------------
+ * The fused path keeps x (K), the running residual r = A x - b (N), d = diag(A^T A) and
+ * 1/d on the device.  Replaces the host state of ClassLasso.run (lasso.py:210-219) and
+ * the device state of ClassLassoCB_v2 (lasso.py:367-375,477-500).
+ * set_problem : upload b (host, N doubles), compute d on the device (lasso.py:29-30),
+ *               set x = 0 and r = -b (lasso.py:89-91,105).
+ * set_x       : warm start (not in the reference): x <- x0
+ *               (host, K doubles), r <- A x0 - b.
+ * get_x/get_r : copy x (K doubles) / r (N doubles) to the host. */
+int b200l_set_problem(b200l_ctx *ctx, const double *b_host);
+int b200l_reset(b200l_ctx *ctx);              /* x = 0, r = -b, stop counter = 0 */
+int b200l_set_x(b200l_ctx *ctx, const double *x_host);
+int b200l_get_x(b200l_ctx *ctx, double *x_host);
+int b200l_get_r(b200l_ctx *ctx, double *r_host);
+
+/* -- the hot path -------------------------------------------------------------------
+ * Runs up to `nsteps` iterations of the reference loop body (lasso.py:102-157 /
+ * :228-278 / :508-599) in ONE persistent cooperative kernel: for each step
+ *   m = order[step]                                            (lasso.py:104)
+ *   g = A_m^T r ; u = d_m*x_m - g ; Bx = S_mu(u)/d_m ; D = Bx - x_m   (:107-119)
+ *   q = A_m D ; gamma = clip(-(r.q + mu(|Bx|_1-|x_m|_1))/|q|^2, 0, 1)  (:121-136)
+ *   err = |g - clip(g - x_m, -mu, mu)|_inf and the all-blocks stop rule (:138-150)
+ *   x_m += gamma D ; r += gamma q                                (:153-155)
+ * order_host : nsteps block indices, or NULL for the cyclic order (t % nblocks)
+ *              continuing from the context's step counter.
+ * err_bound  : < 0 disables the stop rule (the reference's non-float ERR_BOUND,
+ *              lasso.py:74-77).
+ * err_hist_host / time_hist_host : optional per-step outputs (nsteps doubles each):
+ *              the error criterion of the step (err_iter, lasso.py:54-58) and seconds
+ *              since kernel start at the end of the step (time_iter, lasso.py:60-62).
+ * steps_done : loop bodies entered (the reference's t+1 at exit, lasso.py:64-68).
+ * stopped    : 1 if the stop rule fired (the breaking step's update is NOT applied,
+ *              lasso.py:141-153).
+ * kernel_ms  : device time of the launch measured with CUDA events on the stream.
+ * If steps_done, stopped, kernel_ms and both hist pointers are all NULL the call does
+ * not synchronise. */
+int b200l_run(b200l_ctx *ctx, const int32_t *order_host, int64_t nsteps, double mu,
+              double err_bound, double *err_hist_host, double *time_hist_host,
+              int64_t *steps_done, int32_t *stopped, double *kernel_ms);
+
+/* launch geometry of the fused kernel for this context (for DESIGN/bench reporting) */
+int b200l_run_config(b200l_ctx *ctx, int32_t *grid, int32_t *threads, int32_t *smem_bytes,
+                     int32_t *tile_rows, int32_t *ring_slots, int32_t *tiles_per_slab);
+/* tunables: ring slot bytes target (0 = default), kept tiles per slab (-1 = auto) */
+int b200l_set_tuning(b200l_ctx *ctx, int32_t slot_bytes_target, int32_t keep_tiles);
+
+/* 0.5*|r|^2 + mu*|x|_1 from the device state (lasso.py:46-47 with the running residual) */
+int b200l_objective(b200l_ctx *ctx, double mu, double *value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200LASSO_H */
