@@ -305,7 +305,9 @@ def main_gpu(args):
 
     # ---- e2e: through ClassLasso.run(), host b in, host x out -------------------------
     e2e_sweeps = args.e2e_sweeps
-    solver = lasso.ClassLasso(cal, d_ATA, store, b, mu, BLOCK, BLOCK * e2e_sweeps)
+    class HostShape:            # the solver only needs A.shape on the fused path (lasso.py:32)
+        shape = (N, K)
+    solver = lasso.ClassLasso(cal, d_ATA, HostShape, b, mu, BLOCK, BLOCK * e2e_sweeps)
     for _ in range(2):
         solver.run(SILENCE=True)
     barrier()

@@ -196,7 +196,11 @@ class ClassLasso(ClassLassoCPU):
         """Whole solve in one persistent kernel (b200l_run)."""
         lib = self.gpu_cal._lib
         ctx = self.gpu_cal.ctx
-        K = self.A_SHAPE[1]
+        K = self.gpu_cal.MAT_WIDTH_ALL
+        if tuple(self.A_SHAPE) != (self.gpu_cal.MAT_HEIGHT, K) or self.BLOCK != self.gpu_cal.Block:
+            raise ValueError("A%s / BLOCK=%d do not match the GPU_Calculation (%d x %d, %d blocks)"
+                             % (tuple(self.A_SHAPE), self.BLOCK, self.gpu_cal.MAT_HEIGHT, K,
+                                self.gpu_cal.Block))
         bounded = isinstance(ERR_BOUND, float)
         order = np.fromiter((self.index_get(t) for t in range(self.ITER_MAX)),
                             dtype=np.int32, count=self.ITER_MAX)
