@@ -152,28 +152,97 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
-// grid-wide barrier over the consumer threads of all (co-resident) CTAs
-__device__ __forceinline__ void grid_sync(unsigned long long *bar, unsigned long long &target,
-                                          int G, int tid) {
-    cbar();
-    if (tid == 0) {
-        target += (unsigned long long)G;
-        __threadfence();
-        atomicAdd(bar, 1ULL);
-        while (ld_acquire_u64(bar) < target) {
-        }
-    }
-    cbar();
+// ------------------------------------------------------------------------------------
+// cross-CTA exchange: self-validating "LL" words
+// ------------------------------------------------------------------------------------
+// Every 8-byte half of a 16-byte word carries 32 bits of payload and a 32-bit tag (the
+// context-wide step number, never 0).  A reader polls the word itself until both tags
+// match, so the exchange needs no separate flag, fence or atomic: naturally aligned 64-bit
+// accesses are single-copy atomic and each half validates itself.  One store latency plus
+// one load latency per exchange, instead of store / fence / atomic / poll / load.
+__device__ __forceinline__ ulonglong2 ll_ld(const ulonglong2 *p) {
+    ulonglong2 v;
+    asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
 }
+__device__ __forceinline__ void ll_st(ulonglong2 *p, unsigned long long a, unsigned long long b) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ unsigned long long ll_ld1(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ll_st1(unsigned long long *p, unsigned long long a) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(a) : "memory");
+}
+__device__ __forceinline__ unsigned long long ll_pack(uint32_t payload, uint32_t tag) {
+    return ((unsigned long long)tag << 32) | (unsigned long long)payload;
+}
+__device__ __forceinline__ bool ll_ok(const ulonglong2 v, uint32_t tag) {
+    return (uint32_t)(v.x >> 32) == tag && (uint32_t)(v.y >> 32) == tag;
+}
+__device__ __forceinline__ double ll_dbl(const ulonglong2 v) {
+    return __hiloint2double((int)(uint32_t)v.y, (int)(uint32_t)v.x);
+}
+__device__ __forceinline__ void ll_st_dbl(ulonglong2 *p, double a, uint32_t tag) {
+    ll_st(p, ll_pack((uint32_t)__double2loint(a), tag), ll_pack((uint32_t)__double2hiint(a), tag));
+}
+
+// per-type encoding of the exchanged values: (g_r, g_q) of a column as two floats in one
+// word or one word per double; the step D as one 8-byte word per float or one 16-byte word
+// per double
+template <typename T> struct LLW;
+template <> struct LLW<float> {
+    static constexpr int WPC = 1;
+    __device__ static __forceinline__ void put(ulonglong2 *p, float a, float b, uint32_t tag) {
+        ll_st(p, ll_pack(__float_as_uint(a), tag), ll_pack(__float_as_uint(b), tag));
+    }
+    __device__ static __forceinline__ void get(const ulonglong2 (&v)[1], double &a, double &b) {
+        a = (double)__uint_as_float((uint32_t)v[0].x);
+        b = (double)__uint_as_float((uint32_t)v[0].y);
+    }
+    __device__ static __forceinline__ void dput(void *base, int j, float v, uint32_t tag) {
+        ll_st1(reinterpret_cast<unsigned long long *>(base) + j, ll_pack(__float_as_uint(v), tag));
+    }
+    __device__ static __forceinline__ bool dtry(const void *base, int j, uint32_t tag, float &out) {
+        const unsigned long long v = ll_ld1(reinterpret_cast<const unsigned long long *>(base) + j);
+        out = __uint_as_float((uint32_t)v);
+        return (uint32_t)(v >> 32) == tag;
+    }
+};
+template <> struct LLW<double> {
+    static constexpr int WPC = 2;
+    __device__ static __forceinline__ void put(ulonglong2 *p, double a, double b, uint32_t tag) {
+        ll_st_dbl(p, a, tag);
+        ll_st_dbl(p + 1, b, tag);
+    }
+    __device__ static __forceinline__ void get(const ulonglong2 (&v)[2], double &a, double &b) {
+        a = ll_dbl(v[0]);
+        b = ll_dbl(v[1]);
+    }
+    __device__ static __forceinline__ void dput(void *base, int j, double v, uint32_t tag) {
+        ll_st_dbl(reinterpret_cast<ulonglong2 *>(base) + j, v, tag);
+    }
+    __device__ static __forceinline__ bool dtry(const void *base, int j, uint32_t tag, double &out) {
+        const ulonglong2 v = ll_ld(reinterpret_cast<const ulonglong2 *>(base) + j);
+        out = ll_dbl(v);
+        return ll_ok(v, tag);
+    }
+};
+
+constexpr int NTTRACE = 96;        // per-tile stamps: 6 groups of 16 (see b200lasso.h)
+constexpr int NTRACE = 12;         // time stamps per CTA and step of b200l_run_traced
+constexpr int PPL = 5;             // source CTAs per lane in the gather: grid <= 32 * PPL
+constexpr int GMAX = 32 * PPL;     // = 160
 
 // ------------------------------------------------------------------------------------
 // fused kernel parameters
 // ------------------------------------------------------------------------------------
 struct Ctl {
-    double rq, qq, l1, err;
     unsigned long long kc, k_issued;
     int stop;
-    int pad;
+    int abort;
 };
 
 struct RunParams {
@@ -185,32 +254,95 @@ struct RunParams {
     const double *d;     // [nblocks][ld]
     const double *drec;  // [nblocks][ld]
     double *r;           // [N]
-    void *gpart;         // [G][2][ld] of T
-    double *spart;       // [G][4]
-    double *dglob;       // [ld]
-    unsigned long long *bar;
+    ulonglong2 *gLL;     // [G readers][G writers][cs][WPC]  partial block gradients
+    ulonglong2 *sLL;     // [G][4]                           per-CTA line-search scalars
+    void *dLL;           // [ld]                             the step D
+    int *abort_flag;
     const int32_t *order;
     int64_t nsteps, step0;
     double mu, err_bound;
     int32_t bounded;
     double *err_hist;
     unsigned long long *time_hist;
-    long long *state;     // [0] steps_done [1] stopped [2] block_cnt
+    long long *state;     // [0] steps_done [1] stopped [2] block_cnt [3] aborted
     double *gamma_state;  // [0] last gamma
+    unsigned long long *trace;  // optional [G][nsteps][NTRACE] phase time stamps (ns since start)
+    unsigned long long *ttrace; // optional [G][nsteps][NTTRACE] per-tile time stamps (absolute ns)
+    uint32_t tag_base;
+    int32_t dbg;          // diagnostics only: 1 skip exchange waits, 2 skip pass-1 math, 4 skip pass-2 math
+    unsigned long long wait_limit_ns;
     // geometry
-    int32_t TR, S, slot_bytes, cs, npg, wpr, nrg, ncg, rows_max, keep;
+    int32_t TR, S, slot_bytes, cs, cs_shift, wpr, nrg, ncg, rows_pad, keep, inflight;
     // shared-memory offsets
-    int32_t off_bar, off_ctl, off_rloc, off_qloc, off_rT, off_qT, off_delta, off_redT, off_red64,
-        off_small, off_qpart;
+    int32_t off_bar, off_ctl, off_rloc, off_qloc, off_rT, off_qT, off_delta, off_redT, off_colsum,
+        off_stage, off_small, off_qpart, ring_bytes;
+};
+
+// bounded spinning: returns false when the wait has to be abandoned (a peer timed out or
+// this wait exceeded the limit) so that a lost CTA can never hang the device
+struct Waiter {
+    volatile int *gabort;
+    volatile int *sabort;
+    unsigned long long limit_ns;
+    unsigned spins;
+    unsigned long long t0;
+    __device__ __forceinline__ void begin() { spins = 0; t0 = 0; }
+    __device__ __noinline__ bool again() {
+        ++spins;
+        if (spins > 8u) __nanosleep(20);
+        if ((spins & 63u) == 0u && *sabort) return false;
+        if ((spins & 1023u) == 0u) {
+            if (*gabort) { *sabort = 1; return false; }
+            const unsigned long long now = globaltimer_ns();
+            if (t0 == 0) {
+                t0 = now;
+            } else if (now - t0 > limit_ns) {
+                *gabort = 1;
+                *sabort = 1;
+                return false;
+            }
+        }
+        return true;
+    }
+};
+
+// load 4 consecutive entries of a T vector in shared memory (16-byte aligned for float)
+__device__ __forceinline__ void load4(const float *p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4 *>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load4(const double *p, double (&v)[4]) {
+    const double2 a = *reinterpret_cast<const double2 *>(p);
+    const double2 b = *reinterpret_cast<const double2 *>(p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ float4 vzero(float4) { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ double2 vzero(double2) { return make_double2(0.0, 0.0); }
+__device__ __forceinline__ void vunpack(const float4 v, float (&a)[4]) { a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
+__device__ __forceinline__ void vunpack(const double2 v, double (&a)[2]) { a[0] = v.x; a[1] = v.y; }
+
+// ring cursor: slot index and phase parity advance without divisions
+struct Cursor {
+    int slot;
+    uint32_t phase;
+    __device__ __forceinline__ void advance(int S) {
+        if (++slot == S) { slot = 0; phase ^= 1u; }
+    }
 };
 
 // ------------------------------------------------------------------------------------
 // the fused persistent kernel, row-major blocks (nblocks, N, ld)
 // ------------------------------------------------------------------------------------
-template <typename T, int CPT>
+// The per-step code is kept small on purpose (rolled loops, one copy of every phase): it
+// runs once per block step and has to stay resident in the instruction cache.
+// CPT : column groups (16-byte vectors) per thread in pass 1 (ld/V <= CPT*NTC)
+// DK  : column groups per lane kept in registers for the step D in pass 2 (0: read D from smem)
+template <typename T, int CPT, int DK>
 __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunParams p) {
     using VecT = typename VT<T>::type;
+    using LL = LLW<T>;
     constexpr int V = VT<T>::V;
+    constexpr int WPC = LL::WPC;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *ring = smem;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + p.off_bar);
@@ -222,9 +354,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
     T *qT = reinterpret_cast<T *>(smem + p.off_qT);
     T *delta_s = reinterpret_cast<T *>(smem + p.off_delta);
     T *redT = reinterpret_cast<T *>(smem + p.off_redT);
-    double *red64 = reinterpret_cast<double *>(smem + p.off_red64);
+    double2 *colsum = reinterpret_cast<double2 *>(smem + p.off_colsum);   // [4 + cs]
+    uint2 *stage = reinterpret_cast<uint2 *>(smem + p.off_stage);         // gathered payloads
     double *l1s = reinterpret_cast<double *>(smem + p.off_small);
     double *es = l1s + MAX_CS;
+    double *lsred = l1s + 2 * MAX_CS;     // [2][NW] line-search partials of the warps
     double *qpart = reinterpret_cast<double *>(smem + p.off_qpart);
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
@@ -235,42 +369,69 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
     const int64_t row0 = (int64_t)c * base + (c < rem ? c : rem);
     const int TR = p.TR, S = p.S, ld = p.ld, ncg = p.ncg;
     const int nt = (rows_c + TR - 1) / TR;
+    const int keep = min(p.keep, nt);        // last `keep` tiles of pass 1 stay in the ring for pass 2
+    const int nreload = nt - keep;
     const T *Aall = reinterpret_cast<const T *>(p.A);
 
+    // the ring starts zero-filled: rows of a ragged last tile that no copy ever wrote are
+    // multiplied by r = q = 0 in pass 1 and must therefore be finite
+    for (int i = tid; i < p.ring_bytes / 16; i += NTHREADS)
+        reinterpret_cast<uint4 *>(ring)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(full + s, 1);
             mbar_init(empty + s, NW);
         }
         ctl->stop = 0;
+        ctl->abort = 0;
         ctl->kc = 0;
         ctl->k_issued = 0;
         fence_mbar_init();
     }
+    // order the generic-proxy zero fill before the async-proxy (TMA) writes into the ring
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
     if (wid == NW) {
         // ============================ producer warp ================================
         if (lane == 0) {
-            unsigned long long k = 0;
+            unsigned long long k = 0, kd = 0;   // tiles issued / tiles known to have landed
+            Cursor cur{0, 1u};   // waits on "empty" with the inverted parity
+            Cursor dcur{0, 0u};  // oldest tile not yet known to have landed
+            const unsigned long long max_inflight = (unsigned long long)p.inflight;
             volatile int *stopf = &ctl->stop;
             bool live = true;
+            int mc = (int)(p.step0 % p.nblocks);
             for (int64_t step = 0; step < p.nsteps && live; ++step) {
-                const int m = p.order ? p.order[step] : (int)((p.step0 + step) % p.nblocks);
+                const int m = p.order ? p.order[step] : mc;
+                if (++mc == p.nblocks) mc = 0;
                 const T *Ab = Aall + (int64_t)m * p.blk_stride + row0 * (int64_t)ld;
                 for (int pass = 0; pass < 2 && live; ++pass) {
-                    for (int t = 0; t < nt; ++t) {
-                        const int slot = (int)(k % (unsigned)S);
-                        const uint32_t ph = (uint32_t)(((k / (unsigned)S) & 1ULL) ^ 1ULL);
-                        while (!mbar_try_wait(empty + slot, ph)) {
+                    const int ntl = pass == 0 ? nt : nreload;
+                    for (int t = 0; t < ntl; ++t) {
+                        // pacing: a bounded number of bulk copies in flight
+                        while (k - kd >= max_inflight) {
+                            if (mbar_try_wait(full + dcur.slot, dcur.phase)) {
+                                dcur.advance(S);
+                                ++kd;
+                            } else if (*stopf) {
+                                live = false;
+                                break;
+                            }
+                        }
+                        if (!live) break;
+                        while (!mbar_try_wait(empty + cur.slot, cur.phase)) {
                             if (*stopf) { live = false; break; }
                         }
                         if (!live) break;
                         const int rows_t = min(TR, rows_c - t * TR);
                         const uint32_t bytes = (uint32_t)rows_t * (uint32_t)ld * (uint32_t)sizeof(T);
-                        mbar_expect_tx(full + slot, bytes);
-                        tma_bulk_g2s(ring + (size_t)slot * p.slot_bytes, Ab + (int64_t)t * TR * ld,
-                                     bytes, full + slot);
+                        mbar_expect_tx(full + cur.slot, bytes);
+                        tma_bulk_g2s(ring + (size_t)cur.slot * p.slot_bytes, Ab + (int64_t)t * TR * ld,
+                                     bytes, full + cur.slot);
+                        if (p.ttrace && t < 16)
+                            p.ttrace[((size_t)c * p.nsteps + step) * NTTRACE + 64 + pass * 16 + t] = globaltimer_ns();
+                        cur.advance(S);
                         ++k;
                     }
                 }
@@ -287,25 +448,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
             q_loc[i] = 0.0;
             qT[i] = (T)0;
         }
+        for (int i = rows_c + tid; i < p.rows_pad; i += NTC) { rT[i] = (T)0; qT[i] = (T)0; }
         cbar();
 
-        unsigned long long bar_target = 0;
         unsigned long long kc = 0;
+        Cursor cur{0, 0u};
         bool have_prev = false;
         int m_prev = 0;
         int64_t step_prev = -1;
         double sp_rq = 0, sp_qq = 0, sp_l1 = 0, sp_err = 0;  // thread 0 only
-        double dprev = 0, xprev = 0;                          // tid < cs
+        double dprev = 0, xprev = 0;                          // column threads
         int64_t prev_idx = -1;
         long long block_cnt = p.state[2];
         double gamma_last = p.gamma_state[0];
-        int stopped = 0;
+        int stopped = 0, aborted = 0;
         int64_t steps_done = 0;
         const unsigned long long t_start = globaltimer_ns();
-        const int cs = p.cs, npg = p.npg, wpr = p.wpr, nrg = p.nrg;
+        const int cs = p.cs, wpr = p.wpr, nrg = p.nrg;
         const double mu = p.mu;
-        T *gp = reinterpret_cast<T *>(p.gpart);
+        const uint32_t tag0 = p.tag_base;
+        const ulonglong2 *inbox = p.gLL + (size_t)c * G * cs * WPC;
+        Waiter waiter{p.abort_flag, &ctl->abort, p.wait_limit_ns, 0u, 0ull};
+        unsigned long long *trace =
+            (p.trace != nullptr && tid == 0) ? p.trace + (size_t)c * p.nsteps * NTRACE : nullptr;
+        unsigned long long *ttrace =
+            (p.ttrace != nullptr && tid == 0) ? p.ttrace + (size_t)c * p.nsteps * NTTRACE : nullptr;
+        int mc = (int)(p.step0 % p.nblocks);
 
+        // pass-1 mapping: thread = (column group cg0 [+k*NTC], row-quad group rg of nrg)
         int cg0, rg;
         bool p1_active;
         if (CPT == 1) {
@@ -317,226 +487,368 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
             cg0 = tid;
             rg = 0;
         }
+        // pass-2 mapping: warp = (row rr0 [+rstep], column part); lane strides column groups
+        const int part = (wpr > 1) ? (wid % wpr) : 0;
+        const int rr0 = (wpr > 1) ? (wid / wpr) : wid;
+        const int rstep = (wpr > 1) ? TR : NW;
+        const int cstride = 32 * wpr;
+        const int cgl0 = lane + 32 * part;
+        // stage-2 mapping: thread jl < cs owns column j0+jl of every block
+        const int j0 = c * cs;
+        const int jcol = j0 + tid;
+        const bool colthr = tid < cs && jcol < ld;
+        const bool has_col = colthr && jcol < p.w;
+        VecT dreg[DK > 0 ? DK : 1];
 
-        // resolves the pending step: reduces the per-CTA scalars, applies the stop rule,
-        // computes gamma.  Returns false when the stop rule fired.
-        auto resolve_prev = [&](double &gamma_out) -> bool {
-            if (wid == 0) {
-                double a = 0, b = 0, l = 0, e = 0;
-                for (int pp = lane; pp < G; pp += 32) {
-                    a += __ldcg(p.spart + 4 * pp + 0);
-                    b += __ldcg(p.spart + 4 * pp + 1);
-                    l += __ldcg(p.spart + 4 * pp + 2);
-                    e = fmax(e, __ldcg(p.spart + 4 * pp + 3));
+        for (int64_t step = 0;; ++step) {
+            // the iteration after the last step only resolves the pending step
+            const bool drain = step == p.nsteps;
+            if (drain && !have_prev) break;
+            const int m = drain ? 0 : (p.order ? p.order[step] : mc);
+            if (++mc == p.nblocks) mc = 0;
+            const uint32_t tag = tag0 + (uint32_t)step + 1u;
+            if (trace && !drain) trace[step * NTRACE + 0] = globaltimer_ns() - t_start;
+
+            // prox operands of my column: issued now, consumed after the gather
+            const int64_t idx = (int64_t)m * ld + jcol;
+            double xj = 0.0, dj = 0.0, drj = 0.0;
+            int keep_slot0 = 0;                 // ring slot of the first kept tile
+            if (!drain) {
+                if (has_col) {
+                    dj = p.d[idx];
+                    drj = p.drec[idx];
+                    if (idx != prev_idx) xj = __ldcg(p.x + idx);
                 }
-                a = warp_sum(a); b = warp_sum(b); l = warp_sum(l); e = warp_max(e);
-                if (lane == 0) { ctl->rq = a; ctl->qq = b; ctl->l1 = l; ctl->err = e; }
-            }
-            cbar();
-            const double rq = ctl->rq, qq = ctl->qq, l1 = ctl->l1, err = ctl->err;
-            if (c == 0 && tid == 0 && p.err_hist) p.err_hist[step_prev] = err;
-            if (p.bounded) {                                   // lasso.py:141-150
-                if (err < p.err_bound) ++block_cnt;
-                if (m_prev == p.nblocks - 1) {
-                    if (block_cnt == p.nblocks) return false;
-                    block_cnt = 0;
-                }
-            }
-            if (qq != 0.0)                                     // lasso.py:133-136
-                gamma_last = fmin(fmax(-(rq + mu * l1) / qq, 0.0), 1.0);
-            gamma_out = gamma_last;
-            return true;
-        };
 
-        for (int64_t step = 0; step < p.nsteps; ++step) {
-            const int m = p.order ? p.order[step] : (int)((p.step0 + step) % p.nblocks);
-            steps_done = step + 1;
+                // ---------------- pass 1: partial (A_m^T r, A_m^T q) over the slab ------
+                T ar[CPT][V], aq[CPT][V];
+#pragma unroll
+                for (int k = 0; k < CPT; ++k)
+#pragma unroll
+                    for (int e = 0; e < V; ++e) { ar[k][e] = (T)0; aq[k][e] = (T)0; }
 
-            // -------------------- pass 1: partial (A_m^T r, A_m^T q) over the slab ----
-            T ar[CPT][V], aq[CPT][V];
+#pragma unroll 1
+                for (int t = 0; t < nt; ++t, ++kc) {
+                    mbar_wait(full + cur.slot, cur.phase);
+                    if (ttrace && t < 16) ttrace[step * NTTRACE + t] = globaltimer_ns();
+                    const T *tile = reinterpret_cast<const T *>(ring + (size_t)cur.slot * p.slot_bytes);
+                    const int rows_t = min(TR, rows_c - t * TR);
+                    const T *rTt = rT + t * TR, *qTt = qT + t * TR;
+                    if (p1_active && !(p.dbg & 2)) {
+                        if (TR >= 4) {
+                            // whole quads: rows past rows_t hold finite stale data and meet r = q = 0
+                            const int nquad = (rows_t + 3) >> 2;
+#pragma unroll 1
+                            for (int q4 = rg; q4 < nquad; q4 += nrg) {
+                                T rv[4], qv[4];
+                                load4(rTt + 4 * q4, rv);
+                                load4(qTt + 4 * q4, qv);
+                                const T *trow = tile + (size_t)(4 * q4) * ld + cg0 * V;
 #pragma unroll
-            for (int k = 0; k < CPT; ++k)
+                                for (int k = 0; k < CPT; ++k) {
+                                    if (CPT == 1 || cg0 + k * NTC < ncg) {
+                                        VecT v[4];
 #pragma unroll
-                for (int e = 0; e < V; ++e) { ar[k][e] = (T)0; aq[k][e] = (T)0; }
-
-            for (int t = 0; t < nt; ++t, ++kc) {
-                const int slot = (int)(kc % (unsigned)S);
-                mbar_wait(full + slot, (uint32_t)((kc / (unsigned)S) & 1ULL));
-                const T *tile = reinterpret_cast<const T *>(ring + (size_t)slot * p.slot_bytes);
-                const int rows_t = min(TR, rows_c - t * TR);
-                const T *rTt = rT + t * TR;
-                const T *qTt = qT + t * TR;
-                if (p1_active) {
-#pragma unroll 4
-                    for (int rr = rg; rr < rows_t; rr += nrg) {
-                        const T rv = rTt[rr], qv = qTt[rr];
-                        const T *trow = tile + (size_t)rr * ld;
+                                        for (int i = 0; i < 4; ++i)
+                                            v[i] = *reinterpret_cast<const VecT *>(trow + (size_t)i * ld + k * NTC * V);
 #pragma unroll
-                        for (int k = 0; k < CPT; ++k) {
-                            const int cg = cg0 + k * NTC;
-                            if (CPT == 1 || cg < ncg) {
-                                const VecT v = *reinterpret_cast<const VecT *>(trow + cg * V);
-                                vfma(ar[k], v, rv);
-                                vfma(aq[k], v, qv);
+                                        for (int i = 0; i < 4; ++i) {
+                                            vfma(ar[k], v[i], rv[i]);
+                                            vfma(aq[k], v[i], qv[i]);
+                                        }
+                                    }
+                                }
+                            }
+                        } else {
+#pragma unroll 1
+                            for (int rr = rg; rr < rows_t; rr += nrg) {
+                                const T rv = rTt[rr], qv = qTt[rr];
+                                const T *trow = tile + (size_t)rr * ld + cg0 * V;
+#pragma unroll
+                                for (int k = 0; k < CPT; ++k) {
+                                    if (CPT == 1 || cg0 + k * NTC < ncg) {
+                                        const VecT v = *reinterpret_cast<const VecT *>(trow + k * NTC * V);
+                                        vfma(ar[k], v, rv);
+                                        vfma(aq[k], v, qv);
+                                    }
+                                }
                             }
                         }
                     }
+                    if (t == nreload) keep_slot0 = cur.slot;
+                    if (t < nreload) {              // not kept: hand the slot back to the producer
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(empty + cur.slot);
+                    }
+                    if (ttrace && t < 16) ttrace[step * NTTRACE + 16 + t] = globaltimer_ns();
+                    cur.advance(S);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(empty + slot);
-            }
-            // combine the row groups of this CTA, publish the partial gradient
-            T *gpc = gp + (size_t)c * 2 * ld;
-            if (nrg > 1) {
+                if (trace) trace[step * NTRACE + 1] = globaltimer_ns() - t_start;
+
+                // combine the row groups of this CTA through shared memory and write the partial
+                // gradient into the readers' inboxes, one column per thread: the cs columns a
+                // reader owns are one contiguous message, so a warp stores whole 128-byte lines
                 if (p1_active) {
-                    *reinterpret_cast<VecT *>(redT + (size_t)(rg * 2 + 0) * ld + cg0 * V) = vpack(ar[0]);
-                    *reinterpret_cast<VecT *>(redT + (size_t)(rg * 2 + 1) * ld + cg0 * V) = vpack(aq[0]);
+#pragma unroll
+                    for (int k = 0; k < CPT; ++k) {
+                        const int cg = cg0 + k * NTC;
+                        if (CPT == 1 || cg < ncg) {
+                            *reinterpret_cast<VecT *>(redT + (size_t)(rg * 2 + 0) * ld + cg * V) = vpack(ar[k]);
+                            *reinterpret_cast<VecT *>(redT + (size_t)(rg * 2 + 1) * ld + cg * V) = vpack(aq[k]);
+                        }
+                    }
                 }
                 cbar();
-                for (int cg = tid; cg < ncg; cg += NTC) {
-                    VecT sr = *reinterpret_cast<const VecT *>(redT + cg * V);
-                    VecT sq = *reinterpret_cast<const VecT *>(redT + (size_t)ld + cg * V);
-                    for (int g2 = 1; g2 < nrg; ++g2) {
-                        sr = vadd(sr, *reinterpret_cast<const VecT *>(redT + (size_t)(g2 * 2 + 0) * ld + cg * V));
-                        sq = vadd(sq, *reinterpret_cast<const VecT *>(redT + (size_t)(g2 * 2 + 1) * ld + cg * V));
+#pragma unroll 1
+                for (int j = tid; j < G * cs; j += NTC) {
+                    T sr = (T)0, sq = (T)0;
+                    if (j < ld) {
+#pragma unroll 1
+                        for (int g2 = 0; g2 < nrg; ++g2) {
+                            sr += redT[(size_t)(g2 * 2 + 0) * ld + j];
+                            sq += redT[(size_t)(g2 * 2 + 1) * ld + j];
+                        }
                     }
-                    __stcg(reinterpret_cast<VecT *>(gpc + cg * V), sr);
-                    __stcg(reinterpret_cast<VecT *>(gpc + ld + cg * V), sq);
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < CPT; ++k) {
-                    const int cg = cg0 + k * NTC;
-                    if (p1_active && cg < ncg) {
-                        __stcg(reinterpret_cast<VecT *>(gpc + cg * V), vpack(ar[k]));
-                        __stcg(reinterpret_cast<VecT *>(gpc + ld + cg * V), vpack(aq[k]));
-                    }
+                    const int rd = j >> p.cs_shift;
+                    const int jj = j & (cs - 1);
+                    LL::put(p.gLL + (((size_t)rd * G + c) * cs + jj) * WPC, sr, sq, tag);
                 }
             }
             if (tid == 0) {
-                __stcg(p.spart + 4 * c + 0, sp_rq);
-                __stcg(p.spart + 4 * c + 1, sp_qq);
-                __stcg(p.spart + 4 * c + 2, sp_l1);
-                __stcg(p.spart + 4 * c + 3, sp_err);
+                ll_st_dbl(p.sLL + (size_t)c * 4 + 0, sp_rq, tag);
+                ll_st_dbl(p.sLL + (size_t)c * 4 + 1, sp_qq, tag);
+                ll_st_dbl(p.sLL + (size_t)c * 4 + 2, sp_l1, tag);
+                ll_st_dbl(p.sLL + (size_t)c * 4 + 3, sp_err, tag);
             }
-            grid_sync(p.bar, bar_target, G, tid);  // ---- B1
+            if (trace && !drain) trace[step * NTRACE + 2] = globaltimer_ns() - t_start;
 
-            // -------------------- resolve the previous step (lazy gamma) -------------
+            // ---------------- gather -------------------------------------------------------
+            // (1) every thread polls a few words of this CTA's contiguous inbox (G*cs columns
+            // words, then the 4*G line-search scalars) until their tags match and drops the
+            // payloads in shared memory; (2) warp vc sums "virtual column" vc over the G sources
+            // in a fixed order (vc < 4: scalar vc of the pending step, else my column vc-4)
+            {
+                const int nin = G * cs * WPC;
+                const int ntot = nin + 4 * G;
+#pragma unroll 1
+                for (int e0 = (drain ? nin : 0) + tid; e0 < ntot; e0 += 4 * NTC) {
+                    ulonglong2 v[4];
+                    unsigned pend = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (e0 + i * NTC < ntot) pend |= 1u << i;
+                    waiter.begin();
+                    for (;;) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int e = e0 + i * NTC;
+                            if (pend & (1u << i)) v[i] = ll_ld(e < nin ? inbox + e : p.sLL + (e - nin));
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if ((pend & (1u << i)) && ll_ok(v[i], tag)) pend &= ~(1u << i);
+                        if (pend == 0 || (p.dbg & 1)) break;
+                        if (!waiter.again()) break;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int e = e0 + i * NTC;
+                        if (e < ntot) stage[e] = make_uint2((uint32_t)v[i].x, (uint32_t)v[i].y);
+                    }
+                }
+                cbar();
+                const int nvc = drain ? 4 : 4 + cs;
+#pragma unroll 1
+                for (int vc = wid; vc < nvc; vc += NW) {
+                    double a = 0.0, b = 0.0;
+#pragma unroll 1
+                    for (int pp = lane; pp < G; pp += 32) {
+                        if (vc < 4) {
+                            const double sv = *reinterpret_cast<const double *>(stage + nin + pp * 4 + vc);
+                            if (vc == 3) a = fmax(a, sv); else a += sv;
+                        } else if (WPC == 1) {
+                            const uint2 w2 = stage[pp * cs + (vc - 4)];
+                            a += (double)__uint_as_float(w2.x);
+                            b += (double)__uint_as_float(w2.y);
+                        } else {
+                            const double *w2 = reinterpret_cast<const double *>(stage + (pp * cs + (vc - 4)) * 2);
+                            a += w2[0];
+                            b += w2[1];
+                        }
+                    }
+                    if (vc == 3) {
+                        a = warp_max(a);
+                    } else {
+                        a = warp_sum(a);
+                        b = warp_sum(b);
+                    }
+                    if (lane == 0) colsum[vc] = make_double2(a, b);
+                }
+            }
+            cbar();
+            if (trace && !drain) trace[step * NTRACE + 3] = trace[step * NTRACE + 4] = globaltimer_ns() - t_start;
+
+            // ---------------- resolve the pending step: error, stop rule, gamma ---------
+            bool go = true;
             double gamma_prev = 0.0;
             if (have_prev) {
-                if (!resolve_prev(gamma_prev)) {
-                    stopped = 1;
-                    steps_done = step_prev + 1;
-                    break;
+                const double rq = colsum[0].x, qq = colsum[1].x, l1 = colsum[2].x, err = colsum[3].x;
+                if (c == 0 && tid == 0 && p.err_hist) p.err_hist[step_prev] = err;
+                if (p.bounded) {                                   // lasso.py:141-150
+                    if (err < p.err_bound) ++block_cnt;
+                    if (m_prev == p.nblocks - 1) {
+                        if (block_cnt == p.nblocks) go = false;
+                        else block_cnt = 0;
+                    }
                 }
+                if (go && qq != 0.0)                               // lasso.py:133-136
+                    gamma_last = fmin(fmax(-(rq + mu * l1) / qq, 0.0), 1.0);
+                gamma_prev = gamma_last;
+            }
+            if (trace && !drain) trace[step * NTRACE + 5] = globaltimer_ns() - t_start;
+
+            // ---------------- my column: apply the pending update, prox, publish D ------
+            if (colthr) {
+                double my_l1 = 0.0, my_err = 0.0, delta = 0.0;
+                if (have_prev && go && prev_idx >= 0) {
+                    const double xn = xprev + gamma_prev * dprev;                // lasso.py:153
+                    __stcg(p.x + prev_idx, xn);
+                    if (idx == prev_idx) xj = xn;
+                } else if (idx == prev_idx) {
+                    xj = xprev;
+                }
+                prev_idx = -1;
+                if (!drain) {
+                    if (has_col && dj > 0.0) {
+                        const double2 cs2 = colsum[4 + tid];
+                        const double g = cs2.x + gamma_prev * cs2.y;
+                        const double u = dj * xj - g;                             // lasso.py:114
+                        const double au = fabs(u) - mu;                           // cpu_calculation.py:5-6
+                        const double soft = au > 0.0 ? copysign(au, u) : 0.0;
+                        const double Bx = drj * soft;                             // lasso.py:117
+                        delta = Bx - xj;                                          // lasso.py:119
+                        my_l1 = fabs(Bx) - fabs(xj);
+                        const double gx = g - xj;                                 // cpu_calculation.py:15-20
+                        const double proj = fmin(fmax(gx, -mu), mu);
+                        my_err = fabs(g - proj);
+                        dprev = delta;
+                        xprev = xj;
+                        prev_idx = idx;
+                    }
+                    LL::dput(p.dLL, jcol, (T)delta, tag);
+                    l1s[tid] = my_l1;
+                    es[tid] = my_err;
+                }
+            }
+            if (trace && !drain) trace[step * NTRACE + 6] = globaltimer_ns() - t_start;
+
+            // ---------------- the step D from all slice owners -------------------------
+            if (!drain) {
+#pragma unroll 1
+                for (int j = tid; j < ld; j += NTC) {
+                    T dv;
+                    waiter.begin();
+                    while (!LL::dtry(p.dLL, j, tag, dv) && !(p.dbg & 1)) {
+                        if (!waiter.again()) break;
+                    }
+                    delta_s[j] = dv;
+                }
+            }
+            cbar();
+            if (trace && !drain) trace[step * NTRACE + 7] = globaltimer_ns() - t_start;
+            if (*(volatile int *)&ctl->abort) {
+                aborted = 1;
+                break;
+            }
+            if (!go) {
+                stopped = 1;
+                steps_done = step_prev + 1;
+                break;
+            }
+            if (have_prev) {
+#pragma unroll 1
                 for (int i = tid; i < rows_c; i += NTC) {
                     const double rn = r_loc[i] + gamma_prev * q_loc[i];   // lasso.py:155
                     r_loc[i] = rn;
                     rT[i] = (T)rn;
                 }
             }
-
-            // -------------------- stage 2: reduce my column slice, prox ----------------
-            const int j0 = c * cs;
-            if (tid < npg * cs) {
-                const int jl = tid % cs, pg = tid / cs, j = j0 + jl;
-                double sr = 0.0, sq = 0.0;
-                if (j < ld) {
-                    for (int pp = pg; pp < G; pp += npg) {
-                        sr += (double)__ldcg(gp + ((size_t)pp * 2 + 0) * ld + j);
-                        sq += (double)__ldcg(gp + ((size_t)pp * 2 + 1) * ld + j);
-                    }
-                }
-                red64[pg * cs + jl] = sr;
-                red64[NTC + pg * cs + jl] = sq;
-            }
-            cbar();
-            if (tid < cs) {
-                double my_l1 = 0.0, my_err = 0.0;
-                if (have_prev && prev_idx >= 0)
-                    __stcg(p.x + prev_idx, xprev + gamma_prev * dprev);      // lasso.py:153
-                prev_idx = -1;
-                const int j = j0 + tid;
-                if (j < ld) {
-                    double delta = 0.0;
-                    if (j < p.w) {
-                        double gr = 0.0, gq = 0.0;
-                        for (int pg = 0; pg < npg; ++pg) {
-                            gr += red64[pg * cs + tid];
-                            gq += red64[NTC + pg * cs + tid];
-                        }
-                        const double g = gr + gamma_prev * gq;
-                        const int64_t idx = (int64_t)m * ld + j;
-                        const double xj = __ldcg(p.x + idx);
-                        const double dj = p.d[idx];
-                        if (dj > 0.0) {
-                            const double u = dj * xj - g;                     // lasso.py:114
-                            const double au = fabs(u) - mu;                   // cpu_calculation.py:5-6
-                            const double soft = au > 0.0 ? copysign(au, u) : 0.0;
-                            const double Bx = p.drec[idx] * soft;             // lasso.py:117
-                            delta = Bx - xj;                                  // lasso.py:119
-                            my_l1 = fabs(Bx) - fabs(xj);
-                            const double gx = g - xj;                         // cpu_calculation.py:15-20
-                            const double proj = fmin(fmax(gx, -mu), mu);
-                            my_err = fabs(g - proj);
-                            dprev = delta;
-                            xprev = xj;
-                            prev_idx = idx;
-                        }
-                    }
-                    __stcg(p.dglob + j, delta);
-                }
-                l1s[tid] = my_l1;
-                es[tid] = my_err;
-            }
-            cbar();
+            if (drain) break;
             if (tid == 0) {
                 double a = 0.0, e = 0.0;
-                for (int i = 0; i < cs; ++i) { a += l1s[i]; e = fmax(e, es[i]); }
+                const int ncol = min(cs, max(0, ld - j0));
+#pragma unroll 1
+                for (int i = 0; i < ncol; ++i) { a += l1s[i]; e = fmax(e, es[i]); }
                 sp_l1 = a;
                 sp_err = e;
             }
-            grid_sync(p.bar, bar_target, G, tid);  // ---- B2
-
-            for (int j = tid; j < ld; j += NTC) delta_s[j] = (T)__ldcg(p.dglob + j);
-            cbar();
-
-            // -------------------- pass 2: q = A_m D over the slab ----------------------
-            for (int t = 0; t < nt; ++t, ++kc) {
-                const int slot = (int)(kc % (unsigned)S);
-                mbar_wait(full + slot, (uint32_t)((kc / (unsigned)S) & 1ULL));
-                const T *tile = reinterpret_cast<const T *>(ring + (size_t)slot * p.slot_bytes);
-                const int rows_t = min(TR, rows_c - t * TR);
-                const int part = (wpr > 1) ? (wid % wpr) : 0;
-                const int rr0 = (wpr > 1) ? (wid / wpr) : wid;
-                const int rstep = (wpr > 1) ? TR : NW;
-                const int cstride = 32 * wpr;
-                for (int rr = rr0; rr < rows_t; rr += rstep) {
-                    const T *trow = tile + (size_t)rr * ld;
-                    T a0 = (T)0, a1 = (T)0;
-                    int cg = lane + 32 * part;
-                    for (; cg + cstride < ncg; cg += 2 * cstride) {
-                        const VecT v0 = *reinterpret_cast<const VecT *>(trow + cg * V);
-                        const VecT d0 = *reinterpret_cast<const VecT *>(delta_s + cg * V);
-                        const VecT v1 = *reinterpret_cast<const VecT *>(trow + (cg + cstride) * V);
-                        const VecT d1 = *reinterpret_cast<const VecT *>(delta_s + (cg + cstride) * V);
-                        a0 += vdot(v0, d0);
-                        a1 += vdot(v1, d1);
-                    }
-                    if (cg < ncg) {
-                        const VecT v0 = *reinterpret_cast<const VecT *>(trow + cg * V);
-                        const VecT d0 = *reinterpret_cast<const VecT *>(delta_s + cg * V);
-                        a0 += vdot(v0, d0);
-                    }
-                    const T qv = warp_sum(a0 + a1);
-                    if (lane == 0) qpart[(size_t)(t * TR + rr) * wpr + part] = (double)qv;
+            if (DK > 0) {
+#pragma unroll
+                for (int k = 0; k < DK; ++k) {
+                    const int cg = cgl0 + k * cstride;
+                    dreg[k] = cg < ncg ? *reinterpret_cast<const VecT *>(delta_s + cg * V) : vzero(VecT());
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(empty + slot);
+            }
+
+            // ---------------- pass 2: q = A_m D over the slab ---------------------------
+            // kept tiles first (already in the ring), then the re-streamed ones
+            {
+                int ks = keep_slot0;
+#pragma unroll 1
+                for (int t2 = 0; t2 < nt; ++t2) {
+                    const bool kept = t2 < keep;
+                    const int t = kept ? nreload + t2 : t2 - keep;
+                    int slot;
+                    if (kept) {
+                        slot = ks;
+                        if (++ks == S) ks = 0;
+                    } else {
+                        mbar_wait(full + cur.slot, cur.phase);
+                        slot = cur.slot;
+                        cur.advance(S);
+                        ++kc;
+                    }
+                    if (ttrace && t2 < 16) ttrace[step * NTTRACE + 32 + t2] = globaltimer_ns();
+                    const T *tile = reinterpret_cast<const T *>(ring + (size_t)slot * p.slot_bytes);
+                    const int rows_t = min(TR, rows_c - t * TR);
+                    if (!(p.dbg & 4)) {
+#pragma unroll 1
+                        for (int rr = rr0; rr < rows_t; rr += rstep) {
+                            const T *trow = tile + (size_t)rr * ld;
+                            T a0 = (T)0, a1 = (T)0;
+                            if (DK > 0) {
+                                VecT v[DK > 0 ? DK : 1];
+#pragma unroll
+                                for (int k = 0; k < DK; ++k) {
+                                    const int cg = min(cgl0 + k * cstride, ncg - 1);   // dreg is 0 past ncg
+                                    v[k] = *reinterpret_cast<const VecT *>(trow + cg * V);
+                                }
+#pragma unroll
+                                for (int k = 0; k < DK; ++k) {
+                                    if (k & 1) a1 += vdot(v[k], dreg[k]); else a0 += vdot(v[k], dreg[k]);
+                                }
+                            } else {
+#pragma unroll 2
+                                for (int cg = cgl0; cg < ncg; cg += cstride) {
+                                    const VecT v0 = *reinterpret_cast<const VecT *>(trow + cg * V);
+                                    const VecT d0 = *reinterpret_cast<const VecT *>(delta_s + cg * V);
+                                    a0 += vdot(v0, d0);
+                                }
+                            }
+                            const T qv = warp_sum(a0 + a1);
+                            if (lane == 0) qpart[(size_t)(t * TR + rr) * wpr + part] = (double)qv;
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty + slot);
+                    if (ttrace && t2 < 16) ttrace[step * NTTRACE + 48 + t2] = globaltimer_ns();
+                }
             }
             cbar();
+            if (trace) trace[step * NTRACE + 8] = globaltimer_ns() - t_start;
             {
                 double trq = 0.0, tqq = 0.0;
+#pragma unroll 1
                 for (int i = tid; i < rows_c; i += NTC) {
                     double q = 0.0;
                     for (int pt = 0; pt < wpr; ++pt) q += qpart[(size_t)i * wpr + pt];
@@ -547,11 +859,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                 }
                 trq = warp_sum(trq);
                 tqq = warp_sum(tqq);
-                if (lane == 0) { red64[wid] = trq; red64[NW + wid] = tqq; }
+                if (lane == 0) { lsred[wid] = trq; lsred[NW + wid] = tqq; }
                 cbar();
-                if (tid == 0) {
-                    double a = 0.0, b = 0.0;
-                    for (int i = 0; i < NW; ++i) { a += red64[i]; b += red64[NW + i]; }
+                if (wid == 0) {
+                    const double a = warp_sum(lane < NW ? lsred[lane] : 0.0);
+                    const double b = warp_sum(lane < NW ? lsred[NW + lane] : 0.0);
                     sp_rq = a;
                     sp_qq = b;
                 }
@@ -559,32 +871,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
             have_prev = true;
             m_prev = m;
             step_prev = step;
+            steps_done = step + 1;
             if (c == 0 && tid == 0 && p.time_hist) p.time_hist[step] = globaltimer_ns() - t_start;
+            if (trace) trace[step * NTRACE + 9] = globaltimer_ns() - t_start;
         }
 
-        // -------------------- resolve the last step ----------------------------------
-        if (!stopped && have_prev) {
-            if (tid == 0) {
-                __stcg(p.spart + 4 * c + 0, sp_rq);
-                __stcg(p.spart + 4 * c + 1, sp_qq);
-                __stcg(p.spart + 4 * c + 2, sp_l1);
-                __stcg(p.spart + 4 * c + 3, sp_err);
-            }
-            grid_sync(p.bar, bar_target, G, tid);
-            double gamma_prev = 0.0;
-            if (!resolve_prev(gamma_prev)) {
-                stopped = 1;
-            } else {
-                for (int i = tid; i < rows_c; i += NTC) r_loc[i] += gamma_prev * q_loc[i];
-                if (tid < cs && prev_idx >= 0) __stcg(p.x + prev_idx, xprev + gamma_prev * dprev);
-            }
-        }
         cbar();
         for (int i = tid; i < rows_c; i += NTC) p.r[row0 + i] = r_loc[i];
         if (c == 0 && tid == 0) {
             p.state[0] = steps_done;
             p.state[1] = stopped;
             p.state[2] = block_cnt;
+            p.state[3] = aborted;
             p.gamma_state[0] = gamma_last;
         }
         if (tid == 0) {
@@ -595,8 +893,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
     __syncthreads();
     // drain TMA copies the producer issued past the stop point
     if (tid == 0) {
-        for (unsigned long long k = ctl->kc; k < ctl->k_issued; ++k)
-            mbar_wait(full + (int)(k % (unsigned)S), (uint32_t)((k / (unsigned)S) & 1ULL));
+        unsigned long long k = ctl->kc;
+        Cursor cur{(int)(k % (unsigned)S), (uint32_t)((k / (unsigned)S) & 1ULL)};
+        for (; k < ctl->k_issued; ++k) {
+            mbar_wait(full + cur.slot, cur.phase);
+            cur.advance(S);
+        }
     }
     __syncthreads();
 }
@@ -726,9 +1028,15 @@ struct b200l_ctx {
     // scratch
     double *vin, *vout, *part;
     int part_chunks;
-    void *gpart;
-    double *spart, *dglob, *gamma_state, *err_hist, *objbuf;
-    unsigned long long *bar, *time_hist;
+    // cross-CTA exchange buffers of the fused kernel (LL words, see above)
+    ulonglong2 *gLL, *sLL;
+    void *dLL;
+    size_t gLL_bytes;
+    int *abort_flag;
+    uint32_t tag_base;            // tags already used by earlier launches
+    double *gamma_state, *err_hist, *objbuf;
+    unsigned long long *time_hist, *trace, *ttrace;
+    int64_t trace_cap, ttrace_cap;
     long long *state;
     int32_t *order;
     int64_t hist_cap, order_cap;
@@ -736,10 +1044,11 @@ struct b200l_ctx {
     int have_problem;
     cudaEvent_t ev0, ev1;
     // tuning
-    int32_t slot_target, keep_tiles;
+    int32_t slot_target, keep_tiles, max_inflight, dbg;
     // cached geometry
     RunParams geo;
-    int grid, smem_bytes, cpt, nt_max;
+    int grid, smem_bytes, cpt, dk, nt_max;
+    unsigned long long wait_limit_ns;
     int geo_valid;
 };
 
@@ -815,6 +1124,8 @@ extern "C" int b200l_ctx_create(b200l_ctx **out, int dtype, int layout, int64_t 
     c->smem_optin = (int)prop.sharedMemPerBlockOptin;
     c->slot_target = 32768;
     c->keep_tiles = -1;
+    c->max_inflight = 0;
+    c->wait_limit_ns = 5000000000ULL;
 
     const int64_t nx = (int64_t)nblocks * c->xld;
     const int64_t vmax = std::max<int64_t>(std::max<int64_t>(N, K), nx) + 64;
@@ -830,12 +1141,11 @@ extern "C" int b200l_ctx_create(b200l_ctx **out, int dtype, int layout, int64_t 
     ALLOC(c->vin, vmax * 8);
     ALLOC(c->vout, vmax * 8);
     ALLOC(c->part, (int64_t)c->part_chunks * part_cols * 8);
-    ALLOC(c->gpart, (int64_t)c->sm_count * 2 * c->xld * c->esize + 256);
-    ALLOC(c->spart, (int64_t)c->sm_count * 4 * 8);
-    ALLOC(c->dglob, c->xld * 8);
+    ALLOC(c->sLL, (int64_t)GMAX * 4 * 16);
+    ALLOC(c->dLL, c->xld * 16);
+    ALLOC(c->abort_flag, 64);
     ALLOC(c->gamma_state, 8);
     ALLOC(c->objbuf, 64);
-    ALLOC(c->bar, 64);
     ALLOC(c->state, 64);
 #undef ALLOC
     CK(cudaMemset(c->x, 0, nx * 8));
@@ -845,6 +1155,9 @@ extern "C" int b200l_ctx_create(b200l_ctx **out, int dtype, int layout, int64_t 
     CK(cudaMemset(c->b, 0, N * 8));
     CK(cudaMemset(c->gamma_state, 0, 8));
     CK(cudaMemset(c->state, 0, 64));
+    CK(cudaMemset(c->sLL, 0, (size_t)GMAX * 4 * 16));
+    CK(cudaMemset(c->dLL, 0, (size_t)c->xld * 16));
+    CK(cudaMemset(c->abort_flag, 0, 64));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
     *out = c;
@@ -855,9 +1168,9 @@ extern "C" int b200l_ctx_destroy(b200l_ctx *c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    void *ptrs[] = {c->x, c->d, c->drec, c->dsum, c->r, c->b, c->vin, c->vout, c->part, c->gpart,
-                    c->spart, c->dglob, c->gamma_state, c->objbuf, c->bar, c->state, c->err_hist,
-                    c->time_hist, c->order};
+    void *ptrs[] = {c->x, c->d, c->drec, c->dsum, c->r, c->b, c->vin, c->vout, c->part, c->gLL,
+                    c->sLL, c->dLL, c->abort_flag, c->gamma_state, c->objbuf, c->state, c->err_hist,
+                    c->time_hist, c->trace, c->ttrace, c->order};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1083,10 +1396,12 @@ extern "C" int b200l_objective(b200l_ctx *c, double mu, double *value) {
 // ------------------------------------------------------------------------------------
 // fused launch
 // ------------------------------------------------------------------------------------
-extern "C" int b200l_set_tuning(b200l_ctx *c, int32_t slot_bytes_target, int32_t keep_tiles) {
+extern "C" int b200l_set_tuning(b200l_ctx *c, int32_t slot_bytes_target, int32_t keep_tiles,
+                                int32_t max_inflight_tiles) {
     if (!c) return fail("ctx is NULL");
     c->slot_target = slot_bytes_target > 0 ? slot_bytes_target : 32768;
     c->keep_tiles = keep_tiles;
+    c->max_inflight = max_inflight_tiles;
     c->geo_valid = 0;
     return 0;
 }
@@ -1094,13 +1409,25 @@ extern "C" int b200l_set_tuning(b200l_ctx *c, int32_t slot_bytes_target, int32_t
 typedef void (*fused_fn)(const RunParams);
 
 template <typename T>
-static fused_fn pick_kernel(int cpt) {
+static fused_fn pick_kernel(int cpt, int dk) {
+    if (dk == 4) {
+        switch (cpt) {
+            case 1: return lasso_fused_rowmajor<T, 1, 4>;
+            case 2: return lasso_fused_rowmajor<T, 2, 4>;
+            case 4: return lasso_fused_rowmajor<T, 4, 4>;
+            default: return nullptr;
+        }
+    }
     switch (cpt) {
-        case 1: return lasso_fused_rowmajor<T, 1>;
-        case 2: return lasso_fused_rowmajor<T, 2>;
-        case 4: return lasso_fused_rowmajor<T, 4>;
+        case 1: return lasso_fused_rowmajor<T, 1, 0>;
+        case 2: return lasso_fused_rowmajor<T, 2, 0>;
+        case 4: return lasso_fused_rowmajor<T, 4, 0>;
         default: return nullptr;
     }
+}
+
+static fused_fn ctx_kernel(const b200l_ctx *c) {
+    return c->dtype == B200L_F32 ? pick_kernel<float>(c->cpt, c->dk) : pick_kernel<double>(c->cpt, c->dk);
 }
 
 static int plan_geometry(b200l_ctx *c) {
@@ -1115,7 +1442,7 @@ static int plan_geometry(b200l_ctx *c) {
     if (rowbytes > 32768)
         return fail("block width w=%d needs %lld-byte rows; the fused kernel supports rows up to 32 KiB "
                     "(use more column blocks)", c->w, (long long)rowbytes);
-    int G = c->sm_count;
+    const int G = std::min(c->sm_count, GMAX);
     const int rows_max = (int)((c->N + G - 1) / G);
     const int ncg = ld / V;
     int cpt = 1;
@@ -1127,31 +1454,43 @@ static int plan_geometry(b200l_ctx *c) {
            TR < std::max(1, rows_max))
         TR *= 2;
     const int wpr = TR >= NW ? 1 : NW / TR;
-    int cs = (int)round_up((ld + G - 1) / G, 32 / es);
+    const int dk_need = (ncg + 32 * wpr - 1) / (32 * wpr);
+    const int dk = dk_need <= 4 ? 4 : 0;
+    // columns of every block owned by one CTA: a power of two (shift/mask addressing)
+    int cs = 1, cs_shift = 0;
+    while (cs * G < ld) { cs *= 2; ++cs_shift; }
     if (cs > MAX_CS) return fail("internal: slice width %d > %d", cs, MAX_CS);
-    const int npg = NTC / cs;
     const int slot_bytes = (int)round_up((int64_t)TR * rowbytes, 128);
     const int rows_pad = (int)round_up(std::max(rows_max, 1), std::max(TR, 8));
 
     int off = 0;
     auto take = [&](int bytes) { int o = off; off += (int)round_up(bytes, 128); return o; };
+    auto fixed_part = [&](RunParams *out) {
+        const int o_bar = take(2 * 64 * 8);                       // barriers (up to 64 slots)
+        const int o_ctl = take((int)sizeof(Ctl));
+        const int o_rloc = take(rows_pad * 8);
+        const int o_qloc = take(rows_pad * 8);
+        const int o_rT = take(rows_pad * es);
+        const int o_qT = take(rows_pad * es);
+        // the step D (written after the gather, read in pass 2) overlays the row-group
+        // partials (written after pass 1, read before the gather): two barriers apart
+        const int o_redT = take(nrg * 2 * ld * es);
+        const int o_delta = o_redT;
+        const int o_colsum = take((4 + cs) * 16);                 // gathered scalars + columns
+        const int o_stage = take((G * cs * (es / 4) + 4 * G) * 8); // payloads of the polled words
+        const int o_small = take((2 * MAX_CS + 2 * NW) * 8);      // l1s, es, lsred
+        const int o_qpart = take(rows_pad * wpr * 8);
+        if (out) {
+            out->off_bar = o_bar; out->off_ctl = o_ctl; out->off_rloc = o_rloc; out->off_qloc = o_qloc;
+            out->off_rT = o_rT; out->off_qT = o_qT; out->off_delta = o_delta; out->off_redT = o_redT;
+            out->off_colsum = o_colsum; out->off_stage = o_stage; out->off_small = o_small;
+            out->off_qpart = o_qpart;
+        }
+    };
     // the ring goes first (offset 0); sized after the fixed part is known
-    int fixed = 0;
-    {
-        off = 0;
-        take(2 * 64 * 8);                 // barriers (up to 64 slots)
-        take((int)sizeof(Ctl));
-        take(rows_pad * 8);               // r_loc
-        take(rows_pad * 8);               // q_loc
-        take(rows_pad * es);              // rT
-        take(rows_pad * es);              // qT
-        take(ld * es);                    // delta
-        take(nrg > 1 ? nrg * 2 * ld * es : 16);   // redT
-        take(2 * NTC * 8);                // red64
-        take(2 * MAX_CS * 8);             // l1s, es
-        take(rows_pad * wpr * 8);         // qpart
-        fixed = off;
-    }
+    off = 0;
+    fixed_part(nullptr);
+    const int fixed = off;
     const int avail = c->smem_optin - fixed;
     int S = avail / slot_bytes;
     if (S > 64) S = 64;
@@ -1162,26 +1501,31 @@ static int plan_geometry(b200l_ctx *c) {
     if (S > 2 * nt_max + 2) S = 2 * nt_max + 2;   // more slots than two passes of tiles is useless
     off = 0;
     take(S * slot_bytes);
-    g.off_bar = take(2 * 64 * 8);
-    g.off_ctl = take((int)sizeof(Ctl));
-    g.off_rloc = take(rows_pad * 8);
-    g.off_qloc = take(rows_pad * 8);
-    g.off_rT = take(rows_pad * es);
-    g.off_qT = take(rows_pad * es);
-    g.off_delta = take(ld * es);
-    g.off_redT = take(nrg > 1 ? nrg * 2 * ld * es : 16);
-    g.off_red64 = take(2 * NTC * 8);
-    g.off_small = take(2 * MAX_CS * 8);
-    g.off_qpart = take(rows_pad * wpr * 8);
+    fixed_part(&g);
     c->smem_bytes = off;
     c->grid = G;
     c->cpt = cpt;
+    c->dk = dk;
     c->nt_max = nt_max;
-    g.TR = TR; g.S = S; g.slot_bytes = slot_bytes; g.cs = cs; g.npg = npg; g.wpr = wpr;
-    g.nrg = nrg; g.ncg = ncg; g.rows_max = rows_max; g.keep = 0;
+    int keep = c->keep_tiles >= 0 ? c->keep_tiles : 0;
+    keep = std::min(keep, std::min(S, nt_max));
+    g.TR = TR; g.S = S; g.slot_bytes = slot_bytes; g.cs = cs; g.cs_shift = cs_shift; g.wpr = wpr;
+    g.ring_bytes = S * slot_bytes;
+    g.nrg = nrg; g.ncg = ncg; g.rows_pad = rows_pad; g.keep = keep;
+    g.inflight = c->max_inflight > 0 ? std::min(c->max_inflight, S) : S;
 
-    fused_fn fn = c->dtype == B200L_F32 ? pick_kernel<float>(cpt) : pick_kernel<double>(cpt);
-    if (!fn) return fail("internal: no kernel for cpt=%d", cpt);
+    // inboxes of the partial block gradients: [G readers][G writers][cs][WPC] LL words
+    const size_t need = (size_t)G * G * cs * (es / 4) * 16;
+    if (c->gLL_bytes < need) {
+        if (c->gLL) CK(cudaFree(c->gLL));
+        c->gLL = nullptr;
+        CK(cudaMalloc((void **)&c->gLL, need));
+        c->gLL_bytes = need;
+        CK(cudaMemsetAsync(c->gLL, 0, need, c->stream));
+    }
+
+    fused_fn fn = ctx_kernel(c);
+    if (!fn) return fail("internal: no kernel for cpt=%d dk=%d", cpt, dk);
     CK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_bytes));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, NTHREADS, c->smem_bytes));
@@ -1206,6 +1550,101 @@ extern "C" int b200l_run_config(b200l_ctx *c, int32_t *grid, int32_t *threads, i
     return 0;
 }
 
+// launches the fused kernel for `nsteps` steps; trace (device) may be NULL
+static int launch_fused(b200l_ctx *c, const int32_t *order_host, int64_t nsteps, double mu,
+                        double err_bound, bool want_err, bool want_time, unsigned long long *trace_dev,
+                        unsigned long long *ttrace_dev, bool timed) {
+    if (nsteps > 0x7fff0000LL) return fail("nsteps=%lld is too large for one launch", (long long)nsteps);
+    if (order_host) {
+        for (int64_t i = 0; i < nsteps; ++i)
+            if (order_host[i] < 0 || order_host[i] >= c->nblocks)
+                return fail("order[%lld]=%d out of range", (long long)i, order_host[i]);
+        if (c->order_cap < nsteps) {
+            if (c->order) CK(cudaFree(c->order));
+            c->order = nullptr;
+            c->order_cap = 0;
+            CK(cudaMalloc((void **)&c->order, (size_t)nsteps * 4));
+            c->order_cap = nsteps;
+        }
+        CK(cudaMemcpyAsync(c->order, order_host, (size_t)nsteps * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    if ((want_err || want_time) && c->hist_cap < nsteps) {
+        if (c->err_hist) CK(cudaFree(c->err_hist));
+        if (c->time_hist) CK(cudaFree(c->time_hist));
+        c->err_hist = nullptr;
+        c->time_hist = nullptr;
+        c->hist_cap = 0;
+        CK(cudaMalloc((void **)&c->err_hist, (size_t)nsteps * 8));
+        CK(cudaMalloc((void **)&c->time_hist, (size_t)nsteps * 8));
+        c->hist_cap = nsteps;
+    }
+    if (want_err) CK(cudaMemsetAsync(c->err_hist, 0, (size_t)nsteps * 8, c->stream));
+    if (want_time) CK(cudaMemsetAsync(c->time_hist, 0, (size_t)nsteps * 8, c->stream));
+    // tags tag_base+1 .. tag_base+nsteps+1 are consumed by this launch; never reuse one
+    if ((uint64_t)c->tag_base + (uint64_t)nsteps + 2 >= 0xffffffffULL) {
+        CK(cudaMemsetAsync(c->gLL, 0, c->gLL_bytes, c->stream));
+        CK(cudaMemsetAsync(c->sLL, 0, (size_t)GMAX * 4 * 16, c->stream));
+        CK(cudaMemsetAsync(c->dLL, 0, (size_t)c->xld * 16, c->stream));
+        c->tag_base = 0;
+    }
+
+    RunParams p = c->geo;
+    p.A = c->A;
+    p.N = c->N;
+    p.blk_stride = c->brows * c->ld;
+    p.w = c->w;
+    p.ld = (int32_t)c->ld;
+    p.nblocks = c->nblocks;
+    p.x = c->x; p.d = c->d; p.drec = c->drec; p.r = c->r;
+    p.gLL = c->gLL; p.sLL = c->sLL; p.dLL = c->dLL; p.abort_flag = c->abort_flag;
+    p.order = order_host ? c->order : nullptr;
+    p.nsteps = nsteps;
+    p.step0 = c->step_counter;
+    p.mu = mu;
+    p.err_bound = err_bound;
+    p.bounded = err_bound >= 0.0 ? 1 : 0;
+    p.err_hist = want_err ? c->err_hist : nullptr;
+    p.time_hist = want_time ? c->time_hist : nullptr;
+    p.state = c->state;
+    p.gamma_state = c->gamma_state;
+    p.trace = trace_dev;
+    p.ttrace = ttrace_dev;
+    p.tag_base = c->tag_base;
+    p.wait_limit_ns = c->wait_limit_ns;
+    p.dbg = c->dbg;
+
+    fused_fn fn = ctx_kernel(c);
+    void *args[] = {(void *)&p};
+    if (timed) CK(cudaEventRecord(c->ev0, c->stream));
+    CK(cudaLaunchCooperativeKernel((const void *)fn, dim3(c->grid), dim3(NTHREADS), args,
+                                   (size_t)c->smem_bytes, c->stream));
+    if (timed) CK(cudaEventRecord(c->ev1, c->stream));
+    c->step_counter += nsteps;
+    c->tag_base += (uint32_t)nsteps + 2u;
+    return 0;
+}
+
+// reads back the launch status; fails when the kernel abandoned a cross-CTA wait
+static int finish_fused(b200l_ctx *c, int64_t *steps_done, int32_t *stopped, double *kernel_ms) {
+    long long st[4];
+    CK(cudaMemcpyAsync(st, c->state, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (st[3]) {
+        CK(cudaMemsetAsync(c->abort_flag, 0, 64, c->stream));
+        CK(cudaMemsetAsync(c->state, 0, 64, c->stream));
+        return fail("fused kernel aborted: a cross-CTA wait exceeded %.1f s (solver state is invalid; call "
+                    "b200l_reset)", (double)c->wait_limit_ns * 1e-9);
+    }
+    if (steps_done) *steps_done = st[0];
+    if (stopped) *stopped = (int32_t)st[1];
+    if (kernel_ms) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        *kernel_ms = (double)ms;
+    }
+    return 0;
+}
+
 extern "C" int b200l_run(b200l_ctx *c, const int32_t *order_host, int64_t nsteps, double mu,
                          double err_bound, double *err_hist_host, double *time_hist_host,
                          int64_t *steps_done, int32_t *stopped, double *kernel_ms) {
@@ -1219,60 +1658,12 @@ extern "C" int b200l_run(b200l_ctx *c, const int32_t *order_host, int64_t nsteps
         if (kernel_ms) *kernel_ms = 0.0;
         return 0;
     }
-    if (order_host) {
-        for (int64_t i = 0; i < nsteps; ++i)
-            if (order_host[i] < 0 || order_host[i] >= c->nblocks)
-                return fail("order[%lld]=%d out of range", (long long)i, order_host[i]);
-        if (c->order_cap < nsteps) {
-            if (c->order) CK(cudaFree(c->order));
-            CK(cudaMalloc((void **)&c->order, (size_t)nsteps * 4));
-            c->order_cap = nsteps;
-        }
-        CK(cudaMemcpyAsync(c->order, order_host, (size_t)nsteps * 4, cudaMemcpyHostToDevice, c->stream));
-    }
-    if ((err_hist_host || time_hist_host) && c->hist_cap < nsteps) {
-        if (c->err_hist) CK(cudaFree(c->err_hist));
-        if (c->time_hist) CK(cudaFree(c->time_hist));
-        CK(cudaMalloc((void **)&c->err_hist, (size_t)nsteps * 8));
-        CK(cudaMalloc((void **)&c->time_hist, (size_t)nsteps * 8));
-        c->hist_cap = nsteps;
-    }
-    if (err_hist_host) CK(cudaMemsetAsync(c->err_hist, 0, (size_t)nsteps * 8, c->stream));
-    if (time_hist_host) CK(cudaMemsetAsync(c->time_hist, 0, (size_t)nsteps * 8, c->stream));
-    CK(cudaMemsetAsync(c->bar, 0, 64, c->stream));
-
-    RunParams p = c->geo;
-    p.A = c->A;
-    p.N = c->N;
-    p.blk_stride = c->brows * c->ld;
-    p.w = c->w;
-    p.ld = (int32_t)c->ld;
-    p.nblocks = c->nblocks;
-    p.x = c->x; p.d = c->d; p.drec = c->drec; p.r = c->r;
-    p.gpart = c->gpart; p.spart = c->spart; p.dglob = c->dglob; p.bar = c->bar;
-    p.order = order_host ? c->order : nullptr;
-    p.nsteps = nsteps;
-    p.step0 = c->step_counter;
-    p.mu = mu;
-    p.err_bound = err_bound;
-    p.bounded = err_bound >= 0.0 ? 1 : 0;
-    p.err_hist = err_hist_host ? c->err_hist : nullptr;
-    p.time_hist = time_hist_host ? c->time_hist : nullptr;
-    p.state = c->state;
-    p.gamma_state = c->gamma_state;
-
-    fused_fn fn = c->dtype == B200L_F32 ? pick_kernel<float>(c->cpt) : pick_kernel<double>(c->cpt);
-    void *args[] = {(void *)&p};
+    if (launch_fused(c, order_host, nsteps, mu, err_bound, err_hist_host != nullptr,
+                     time_hist_host != nullptr, nullptr, nullptr, kernel_ms != nullptr))
+        return 1;
     const bool want_sync = steps_done || stopped || kernel_ms || err_hist_host || time_hist_host;
-    if (kernel_ms) CK(cudaEventRecord(c->ev0, c->stream));
-    CK(cudaLaunchCooperativeKernel((const void *)fn, dim3(c->grid), dim3(NTHREADS), args,
-                                   (size_t)c->smem_bytes, c->stream));
-    if (kernel_ms) CK(cudaEventRecord(c->ev1, c->stream));
-    c->step_counter += nsteps;
     if (!want_sync) return 0;
 
-    long long st[3];
-    CK(cudaMemcpyAsync(st, c->state, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
     std::vector<unsigned long long> tbuf;
     if (err_hist_host)
         CK(cudaMemcpyAsync(err_hist_host, c->err_hist, (size_t)nsteps * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1280,15 +1671,60 @@ extern "C" int b200l_run(b200l_ctx *c, const int32_t *order_host, int64_t nsteps
         tbuf.resize((size_t)nsteps);
         CK(cudaMemcpyAsync(tbuf.data(), c->time_hist, (size_t)nsteps * 8, cudaMemcpyDeviceToHost, c->stream));
     }
-    CK(cudaStreamSynchronize(c->stream));
+    if (finish_fused(c, steps_done, stopped, kernel_ms)) return 1;
     if (time_hist_host)
         for (int64_t i = 0; i < nsteps; ++i) time_hist_host[i] = (double)tbuf[(size_t)i] * 1e-9;
-    if (steps_done) *steps_done = st[0];
-    if (stopped) *stopped = (int32_t)st[1];
-    if (kernel_ms) {
-        float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-        *kernel_ms = (double)ms;
+    return 0;
+}
+
+extern "C" int b200l_run_traced(b200l_ctx *c, int64_t nsteps, double mu, uint64_t *trace_host,
+                                uint64_t *tile_trace_host, int32_t *grid_out, double *kernel_ms) {
+    if (need_A(c)) return 1;
+    if (!c->have_problem) return fail("b200l_set_problem has not been called");
+    if (nsteps <= 0 || !trace_host) return fail("nsteps must be positive and trace_host non-NULL");
+    if (plan_geometry(c)) return 1;
+    const int64_t words = (int64_t)c->grid * nsteps * NTRACE;
+    if (c->trace_cap < words) {
+        if (c->trace) CK(cudaFree(c->trace));
+        c->trace = nullptr;
+        c->trace_cap = 0;
+        CK(cudaMalloc((void **)&c->trace, (size_t)words * 8));
+        c->trace_cap = words;
     }
+    CK(cudaMemsetAsync(c->trace, 0, (size_t)words * 8, c->stream));
+    const int64_t twords = (int64_t)c->grid * nsteps * NTTRACE;
+    if (tile_trace_host) {
+        if (c->ttrace_cap < twords) {
+            if (c->ttrace) CK(cudaFree(c->ttrace));
+            c->ttrace = nullptr;
+            c->ttrace_cap = 0;
+            CK(cudaMalloc((void **)&c->ttrace, (size_t)twords * 8));
+            c->ttrace_cap = twords;
+        }
+        CK(cudaMemsetAsync(c->ttrace, 0, (size_t)twords * 8, c->stream));
+    }
+    if (launch_fused(c, nullptr, nsteps, mu, -1.0, false, false, c->trace,
+                     tile_trace_host ? c->ttrace : nullptr, true))
+        return 1;
+    CK(cudaMemcpyAsync(trace_host, c->trace, (size_t)words * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (tile_trace_host)
+        CK(cudaMemcpyAsync(tile_trace_host, c->ttrace, (size_t)twords * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (finish_fused(c, nullptr, nullptr, kernel_ms)) return 1;
+    if (grid_out) *grid_out = c->grid;
+    return 0;
+}
+
+extern "C" int b200l_set_wait_limit(b200l_ctx *c, double seconds) {
+    if (!c) return fail("ctx is NULL");
+    if (!(seconds > 0.0)) return fail("wait limit must be positive");
+    c->wait_limit_ns = (unsigned long long)(seconds * 1e9);
+    return 0;
+}
+
+// diagnostics only (tools/trace_fused.py): switches parts of the fused kernel off to time
+// the rest; results of a run with flags != 0 are meaningless
+extern "C" int b200l_debug_flags(b200l_ctx *c, int32_t flags) {
+    if (!c) return fail("ctx is NULL");
+    c->dbg = flags;
     return 0;
 }

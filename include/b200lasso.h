@@ -22,6 +22,8 @@ extern "C" {
 #endif
 
 #define B200L_ABI_VERSION 1
+#define B200L_NTRACE 12
+#define B200L_NTTRACE 96
 
 /* arithmetic type of A and of the inner products (vectors and line-search scalars are
  * always kept in double, SURVEY.md section 7 "keep line-search scalars in f64") */
@@ -118,8 +120,32 @@ int b200l_run(b200l_ctx *ctx, const int32_t *order_host, int64_t nsteps, double 
 /* launch geometry of the fused kernel for this context (for DESIGN/bench reporting) */
 int b200l_run_config(b200l_ctx *ctx, int32_t *grid, int32_t *threads, int32_t *smem_bytes,
                      int32_t *tile_rows, int32_t *ring_slots, int32_t *tiles_per_slab);
-/* tunables: ring slot bytes target (0 = default), kept tiles per slab (-1 = auto) */
-int b200l_set_tuning(b200l_ctx *ctx, int32_t slot_bytes_target, int32_t keep_tiles);
+/* tunables: ring slot bytes target (0 = default), tiles of a slab kept in shared memory
+ * between the two passes (-1 = default), bulk copies in flight per CTA (0 = ring size) */
+int b200l_set_tuning(b200l_ctx *ctx, int32_t slot_bytes_target, int32_t keep_tiles,
+                     int32_t max_inflight_tiles);
+
+/* Diagnostics of the hot path.  run_traced runs `nsteps` unbounded steps (cyclic order,
+ * like b200l_run with err_bound < 0) and returns, for every CTA and step,
+ * B200L_NTRACE time stamps in ns since kernel start: [0] step start, [1] pass 1 (A_m^T r)
+ * done, [2] partial gradient published, [3] my columns gathered, [4] partials combined,
+ * [5] pending step resolved (gamma), [6] prox done / D published, [7] D gathered,
+ * [8] pass 2 (A_m D) done, [9] line-search partials done.  trace_host holds
+ * grid*nsteps*B200L_NTRACE uint64 (grid = b200l_run_config's grid, also returned in grid_out).
+ * No counterpart in the reference (its only timer is lasso.py:234-236). */
+int b200l_run_traced(b200l_ctx *ctx, int64_t nsteps, double mu, uint64_t *trace_host,
+                     uint64_t *tile_trace_host, int32_t *grid_out, double *kernel_ms);
+/* tile_trace_host (optional, grid*nsteps*B200L_NTTRACE uint64, absolute ns): per CTA and
+ * step six groups of 16 stamps for the first 16 tiles of the slab: [0..15] pass-1 tile
+ * arrived, [16..31] pass-1 tile consumed, [32..47] pass-2 tile arrived, [48..63] pass-2
+ * tile consumed (consumer warp 0), [64..79] / [80..95] the producer issued the pass-1 /
+ * pass-2 bulk copy of the tile. */
+/* upper bound, in seconds, on any single cross-CTA wait inside the fused kernel (default
+ * 5 s); when exceeded the kernel exits and b200l_run fails instead of hanging the device */
+int b200l_set_wait_limit(b200l_ctx *ctx, double seconds);
+/* diagnostics only: bit 0 skips the exchange waits, bit 1 the pass-1 arithmetic, bit 2 the
+ * pass-2 arithmetic of the fused kernel, to time the remaining parts.  Results are invalid. */
+int b200l_debug_flags(b200l_ctx *ctx, int32_t flags);
 
 /* 0.5*|r|^2 + mu*|x|_1 from the device state (lasso.py:46-47 with the running residual) */
 int b200l_objective(b200l_ctx *ctx, double mu, double *value);

@@ -1,0 +1,106 @@
+#!/usr/bin/env python
+"""Phase breakdown of the fused kernel (b200l_run_traced): per block step, where the time
+of the median / slowest CTA goes.  Diagnostic tool, not a bench (GPU only)."""
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+PHASES = ["pass1 (A^T r)", "publish g", "gather g", "combine", "resolve gamma", "prox+publish D",
+          "gather D", "pass2 (A D)", "line-search partials"]
+
+
+def main():
+    import torch
+    from bench import C2, make_device_instance
+    from convex_optimization_b200 import _lib
+    from convex_optimization_b200.gpu_calculation import GPU_Calculation
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--N", type=int, default=C2["N"])
+    ap.add_argument("--K", type=int, default=C2["K"])
+    ap.add_argument("--block", type=int, default=C2["BLOCK"])
+    ap.add_argument("--dtype", default="float")
+    ap.add_argument("--sweeps", type=int, default=3)
+    ap.add_argument("--slot-bytes", type=int, default=0)
+    ap.add_argument("--keep-tiles", type=int, default=-1)
+    ap.add_argument("--inflight", type=int, default=0)
+    ap.add_argument("--sweep", default="", help="semicolon list of slot,keep,inflight[,dbg] tuples")
+    ap.add_argument("--out", default="")
+    ap.add_argument("--raw", default="", help="prefix for raw trace dumps (.npy)")
+    args = ap.parse_args()
+    N, K, BLOCK = args.N, args.K, args.block
+
+    class Cal(GPU_Calculation):
+        TYPE = args.dtype
+    dev = torch.device("cuda", 0)
+    tdt = torch.float32 if args.dtype == "float" else torch.float64
+    ld = Cal.padded_ld(N, K, BLOCK)
+    store, b, mu = make_device_instance(torch, dev, N, K, BLOCK, 0.01, 2, tdt, ld)
+    cal = Cal.from_device_blocks(store, N, K, BLOCK)
+    lib, ctx = cal._lib, cal.ctx
+    bb = np.ascontiguousarray(b.reshape(-1))
+    NT = _lib.NTRACE
+    combos = [(args.slot_bytes, args.keep_tiles, args.inflight, 0)]
+    if args.sweep:
+        combos = [tuple(int(v) for v in c.split(",")) for c in args.sweep.split(";") if c]
+    results = []
+    for combo in combos:
+        slot, keep, infl = combo[:3]
+        dbg = combo[3] if len(combo) > 3 else 0
+        cal.set_tuning(slot, keep, infl)
+        _lib.check(lib.b200l_debug_flags(ctx, dbg))
+        _lib.check(lib.b200l_set_problem(ctx, _lib.dptr(bb)))
+        geo = cal.run_config()
+        G = geo["grid"]
+        for _ in range(2):
+            _lib.check(lib.b200l_run(ctx, None, BLOCK, float(mu), -1.0, None, None, None, None, None))
+        nsteps = BLOCK * args.sweeps
+        tr = np.zeros((G, nsteps, NT), np.uint64)
+        kms = ctypes.c_double()
+        g_out = ctypes.c_int32()
+        tt = np.zeros((G, nsteps, _lib.NTTRACE), np.uint64) if args.raw else None
+        _lib.check(lib.b200l_run_traced(ctx, nsteps, float(mu),
+                                        tr.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)),
+                                        tt.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)) if tt is not None else None,
+                                        ctypes.byref(g_out), ctypes.byref(kms)))
+        # untraced timing of the same configuration
+        k2 = ctypes.c_double()
+        ts = []
+        for _ in range(5):
+            _lib.check(lib.b200l_run(ctx, None, BLOCK, float(mu), -1.0, None, None, None, None,
+                                     ctypes.byref(k2)))
+            ts.append(k2.value)
+        t = tr.astype(np.float64)[:, :, :10] * 1e-3          # us
+        s = t[:, BLOCK:, :]                        # skip the first sweep of the launch
+        dur = np.diff(s, axis=2)
+        step_len = s[:, 1:, 0] - s[:, :-1, 0]
+        out = {"tuning": {"slot_bytes": slot, "keep": keep, "inflight": infl, "dbg": dbg}, "geo": geo,
+               "ms_per_sweep_traced": kms.value / args.sweeps, "ms_per_sweep": float(np.median(ts)),
+               "sweeps_per_s": 1e3 / float(np.median(ts)),
+               "us_per_block_step": float(step_len.mean()),
+               "phases_us_mean_over_ctas": {n: round(float(dur[:, :, i].mean()), 3) for i, n in enumerate(PHASES)},
+               "phases_us_max_cta": {n: round(float(dur[:, :, i].mean(axis=1).max()), 3) for i, n in enumerate(PHASES)},
+               "phases_us_min_cta": {n: round(float(dur[:, :, i].mean(axis=1).min()), 3) for i, n in enumerate(PHASES)},
+               "skew_us_pass1_end": float((s[:, :, 1].max(axis=0) - s[:, :, 1].min(axis=0)).mean()),
+               "skew_us_step_start": float((s[:, :, 0].max(axis=0) - s[:, :, 0].min(axis=0)).mean())}
+        results.append(out)
+        if args.raw:
+            np.save("%s_%d_%d_%d_%d.npy" % (args.raw, slot, keep, infl, dbg), tr)
+            np.save("%s_tiles_%d_%d_%d_%d.npy" % (args.raw, slot, keep, infl, dbg), tt[::16])
+        print(json.dumps({k: out[k] for k in ("tuning", "ms_per_sweep", "sweeps_per_s", "us_per_block_step",
+                                               "phases_us_mean_over_ctas", "skew_us_pass1_end")}))
+        sys.stdout.flush()
+    out = results if len(results) > 1 else results[0]
+    if args.out:
+        with open(args.out, "w") as f:
+            json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
