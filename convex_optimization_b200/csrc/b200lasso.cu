@@ -52,7 +52,7 @@ static int fail(const char *fmt, ...) {
 // ------------------------------------------------------------------------------------
 // constants / small device helpers
 // ------------------------------------------------------------------------------------
-constexpr int NW = 16;                 // consumer warps
+constexpr int NW = 8;                  // consumer warps
 constexpr int NTC = NW * 32;           // consumer threads
 constexpr int NTHREADS = NTC + 32;     // + one producer warp
 constexpr int MAX_CS = 64;             // max stage-2 slice width (columns per CTA)
@@ -123,6 +123,10 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+// TMA prefetch of a contiguous range into L2 (no shared memory involved; SASS: UBLKPF)
+__device__ __forceinline__ void tma_prefetch_l2(const void *src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cbar() {  // barrier over the consumer threads only
     asm volatile("bar.sync 1, %0;" ::"n"(NTC) : "memory");
 }
@@ -160,21 +164,30 @@ __device__ __forceinline__ double warp_max(double v) {
 // match, so the exchange needs no separate flag, fence or atomic: naturally aligned 64-bit
 // accesses are single-copy atomic and each half validates itself.  One store latency plus
 // one load latency per exchange, instead of store / fence / atomic / poll / load.
-__device__ __forceinline__ ulonglong2 ll_ld(const ulonglong2 *p) {
-    ulonglong2 v;
-    asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
-    return v;
-}
+// Polling loads are plain L2 (.cg) loads on purpose: a batch of them is issued back to back
+// and waited on once.  (ld.volatile makes ptxas interleave each tag check with the next
+// load, which serialises the round trips.)  L1 is bypassed, so a re-read after the opaque
+// Waiter::again() call observes the writer's store.
+__device__ __forceinline__ ulonglong2 ll_ld(const ulonglong2 *p) { return __ldcg(p); }
 __device__ __forceinline__ void ll_st(ulonglong2 *p, unsigned long long a, unsigned long long b) {
     asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
-__device__ __forceinline__ unsigned long long ll_ld1(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
+__device__ __forceinline__ unsigned long long ll_ld1(const unsigned long long *p) { return __ldcg(p); }
 __device__ __forceinline__ void ll_st1(unsigned long long *p, unsigned long long a) {
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(a) : "memory");
+}
+// OR-reduction of a predicate over the consumer threads (named barrier 1)
+__device__ __forceinline__ bool cbar_or(bool pred) {
+    uint32_t out;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.u32 q, %1, 0;\n\t"
+        "barrier.cta.red.or.pred p, 1, %2, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(out)
+        : "r"((uint32_t)pred), "n"(NTC)
+        : "memory");
+    return out != 0;
 }
 __device__ __forceinline__ unsigned long long ll_pack(uint32_t payload, uint32_t tag) {
     return ((unsigned long long)tag << 32) | (unsigned long long)payload;
@@ -202,14 +215,10 @@ template <> struct LLW<float> {
         a = (double)__uint_as_float((uint32_t)v[0].x);
         b = (double)__uint_as_float((uint32_t)v[0].y);
     }
-    __device__ static __forceinline__ void dput(void *base, int j, float v, uint32_t tag) {
-        ll_st1(reinterpret_cast<unsigned long long *>(base) + j, ll_pack(__float_as_uint(v), tag));
+    __device__ static __forceinline__ void dput(ulonglong2 *base, int j, float v, uint32_t tag) {
+        ll_st(base + j, ll_pack(__float_as_uint(v), tag), ll_pack(0u, tag));
     }
-    __device__ static __forceinline__ bool dtry(const void *base, int j, uint32_t tag, float &out) {
-        const unsigned long long v = ll_ld1(reinterpret_cast<const unsigned long long *>(base) + j);
-        out = __uint_as_float((uint32_t)v);
-        return (uint32_t)(v >> 32) == tag;
-    }
+    __device__ static __forceinline__ float dval(const ulonglong2 v) { return __uint_as_float((uint32_t)v.x); }
 };
 template <> struct LLW<double> {
     static constexpr int WPC = 2;
@@ -221,14 +230,10 @@ template <> struct LLW<double> {
         a = ll_dbl(v[0]);
         b = ll_dbl(v[1]);
     }
-    __device__ static __forceinline__ void dput(void *base, int j, double v, uint32_t tag) {
-        ll_st_dbl(reinterpret_cast<ulonglong2 *>(base) + j, v, tag);
+    __device__ static __forceinline__ void dput(ulonglong2 *base, int j, double v, uint32_t tag) {
+        ll_st_dbl(base + j, v, tag);
     }
-    __device__ static __forceinline__ bool dtry(const void *base, int j, uint32_t tag, double &out) {
-        const ulonglong2 v = ll_ld(reinterpret_cast<const ulonglong2 *>(base) + j);
-        out = ll_dbl(v);
-        return ll_ok(v, tag);
-    }
+    __device__ static __forceinline__ double dval(const ulonglong2 v) { return ll_dbl(v); }
 };
 
 constexpr int NTTRACE = 96;        // per-tile stamps: 6 groups of 16 (see b200lasso.h)
@@ -240,6 +245,7 @@ constexpr int GMAX = 32 * PPL;     // = 160
 // fused kernel parameters
 // ------------------------------------------------------------------------------------
 struct Ctl {
+    double sp[4];                    // this CTA's line-search scalars of the pending step
     unsigned long long kc, k_issued;
     int stop;
     int abort;
@@ -254,9 +260,8 @@ struct RunParams {
     const double *d;     // [nblocks][ld]
     const double *drec;  // [nblocks][ld]
     double *r;           // [N]
-    ulonglong2 *gLL;     // [G readers][G writers][cs][WPC]  partial block gradients
-    ulonglong2 *sLL;     // [G][4]                           per-CTA line-search scalars
-    void *dLL;           // [ld]                             the step D
+    ulonglong2 *gLL;     // [G readers][G writers][mw]  scalars + partial block gradients
+    ulonglong2 *dLL;     // [ld]                        the step D
     int *abort_flag;
     const int32_t *order;
     int64_t nsteps, step0;
@@ -272,10 +277,11 @@ struct RunParams {
     int32_t dbg;          // diagnostics only: 1 skip exchange waits, 2 skip pass-1 math, 4 skip pass-2 math
     unsigned long long wait_limit_ns;
     // geometry
-    int32_t TR, S, slot_bytes, cs, cs_shift, wpr, nrg, ncg, rows_pad, keep, inflight;
+    int32_t TR, S, slot_bytes, cs, cs_shift, nrg, ncg, rows_pad, inflight, l2_ahead, l2_pass;
+    int32_t mw, gc, dchunk, nown;   // message words, sources per gather group, D words per fetch, owner CTAs
     // shared-memory offsets
     int32_t off_bar, off_ctl, off_rloc, off_qloc, off_rT, off_qT, off_delta, off_redT, off_colsum,
-        off_stage, off_small, off_qpart, ring_bytes;
+        off_small, off_qpart, ring_bytes;
 };
 
 // bounded spinning: returns false when the wait has to be abandoned (a peer timed out or
@@ -286,7 +292,9 @@ struct Waiter {
     unsigned long long limit_ns;
     unsigned spins;
     unsigned long long t0;
-    __device__ __forceinline__ void begin() { spins = 0; t0 = 0; }
+    long long *diag;              // state[4..7]: where the first abandoned wait happened
+    long long info;
+    __device__ __forceinline__ void begin(long long where = 0) { spins = 0; t0 = 0; info = where; }
     __device__ __noinline__ bool again() {
         ++spins;
         if (spins > 8u) __nanosleep(20);
@@ -297,7 +305,11 @@ struct Waiter {
             if (t0 == 0) {
                 t0 = now;
             } else if (now - t0 > limit_ns) {
-                *gabort = 1;
+                if (atomicExch((int *)gabort, 1) == 0) {
+                    diag[0] = blockIdx.x;
+                    diag[1] = threadIdx.x;
+                    diag[2] = info;
+                }
                 *sabort = 1;
                 return false;
             }
@@ -333,16 +345,79 @@ struct Cursor {
 // ------------------------------------------------------------------------------------
 // the fused persistent kernel, row-major blocks (nblocks, N, ld)
 // ------------------------------------------------------------------------------------
-// The per-step code is kept small on purpose (rolled loops, one copy of every phase): it
-// runs once per block step and has to stay resident in the instruction cache.
-// CPT : column groups (16-byte vectors) per thread in pass 1 (ld/V <= CPT*NTC)
-// DK  : column groups per lane kept in registers for the step D in pass 2 (0: read D from smem)
-template <typename T, int CPT, int DK>
+// 8 consumer warps + 1 producer warp per CTA, one CTA per SM.  Few fat warps on purpose: the
+// passes are bound by instruction issue unless every thread does enough work per tile to
+// amortise the ring handshake (DESIGN.md "why 8 warps").  The per-step code is kept small
+// (rolled loops, one copy of every phase): it runs once per block step and has to stay
+// resident in the instruction cache.
+//
+// per-type arithmetic on one 16-byte column group
+template <typename T> struct Ops;
+template <> struct Ops<float> {
+    struct Acc { float2 lo, hi; };
+    __device__ static __forceinline__ unsigned long long u(const float2 v) {
+        return *reinterpret_cast<const unsigned long long *>(&v);
+    }
+    __device__ static __forceinline__ float2 fma2(const float2 a, const float2 b, const float2 c) {
+        unsigned long long d;   // packed FFMA2: two fp32 fused multiply-adds per instruction
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(u(a)), "l"(u(b)), "l"(u(c)));
+        return *reinterpret_cast<float2 *>(&d);
+    }
+    __device__ static __forceinline__ void zero(Acc &a) { a.lo = make_float2(0.f, 0.f); a.hi = a.lo; }
+    // a += v * s  (four columns of one row)
+    __device__ static __forceinline__ void axpy(Acc &a, const float4 v, const float s) {
+        const float2 ss = make_float2(s, s);
+        a.lo = fma2(make_float2(v.x, v.y), ss, a.lo);
+        a.hi = fma2(make_float2(v.z, v.w), ss, a.hi);
+    }
+    // a += v * d elementwise (partial dot product of one row)
+    __device__ static __forceinline__ void mac(Acc &a, const float4 v, const float4 d) {
+        a.lo = fma2(make_float2(v.x, v.y), make_float2(d.x, d.y), a.lo);
+        a.hi = fma2(make_float2(v.z, v.w), make_float2(d.z, d.w), a.hi);
+    }
+    __device__ static __forceinline__ float hsum(const Acc &a) { return (a.lo.x + a.lo.y) + (a.hi.x + a.hi.y); }
+    __device__ static __forceinline__ float4 pack(const Acc &a) { return make_float4(a.lo.x, a.lo.y, a.hi.x, a.hi.y); }
+};
+template <> struct Ops<double> {
+    struct Acc { double x, y; };
+    __device__ static __forceinline__ void zero(Acc &a) { a.x = 0.0; a.y = 0.0; }
+    __device__ static __forceinline__ void axpy(Acc &a, const double2 v, const double s) {
+        a.x = fma(v.x, s, a.x);
+        a.y = fma(v.y, s, a.y);
+    }
+    __device__ static __forceinline__ void mac(Acc &a, const double2 v, const double2 d) {
+        a.x = fma(v.x, d.x, a.x);
+        a.y = fma(v.y, d.y, a.y);
+    }
+    __device__ static __forceinline__ double hsum(const Acc &a) { return a.x + a.y; }
+    __device__ static __forceinline__ double2 pack(const Acc &a) { return make_double2(a.x, a.y); }
+};
+
+// sums of two values over the warp with 5+1 shuffles: returns the sum of `a` in lanes 0..15
+// and the sum of `b` in lanes 16..31
+template <typename T>
+__device__ __forceinline__ T warp_sum_pair(const T a, const T b, const int lane) {
+    const bool up = lane >= 16;
+    T mine = up ? b : a;
+    const T give = up ? a : b;
+    mine += __shfl_xor_sync(0xffffffffu, give, 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    return mine;
+}
+
+// CPT : column groups (16-byte vectors) per thread in pass 1 (ld/V <= CPT*NTC).  CPT == 1 also
+//       means at most 8 column groups per lane in pass 2, whose slice of the step D then lives
+//       in registers; wider blocks read D from shared memory.
+template <typename T, int CPT>
 __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunParams p) {
     using VecT = typename VT<T>::type;
     using LL = LLW<T>;
+    using OP = Ops<T>;
+    using Acc = typename OP::Acc;
     constexpr int V = VT<T>::V;
     constexpr int WPC = LL::WPC;
+    constexpr int DK = CPT == 1 ? NTC / 32 : 0;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *ring = smem;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + p.off_bar);
@@ -355,11 +430,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
     T *delta_s = reinterpret_cast<T *>(smem + p.off_delta);
     T *redT = reinterpret_cast<T *>(smem + p.off_redT);
     double2 *colsum = reinterpret_cast<double2 *>(smem + p.off_colsum);   // [4 + cs]
-    uint2 *stage = reinterpret_cast<uint2 *>(smem + p.off_stage);         // gathered payloads
+    uint64_t *xbar = full + 127;          // completion of the exchange fetches
     double *l1s = reinterpret_cast<double *>(smem + p.off_small);
     double *es = l1s + MAX_CS;
     double *lsred = l1s + 2 * MAX_CS;     // [2][NW] line-search partials of the warps
-    double *qpart = reinterpret_cast<double *>(smem + p.off_qpart);
+    double *qpart = reinterpret_cast<double *>(smem + p.off_qpart);       // [rows] A_m D
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int c = blockIdx.x, G = gridDim.x;
@@ -369,8 +444,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
     const int64_t row0 = (int64_t)c * base + (c < rem ? c : rem);
     const int TR = p.TR, S = p.S, ld = p.ld, ncg = p.ncg;
     const int nt = (rows_c + TR - 1) / TR;
-    const int keep = min(p.keep, nt);        // last `keep` tiles of pass 1 stay in the ring for pass 2
-    const int nreload = nt - keep;
     const T *Aall = reinterpret_cast<const T *>(p.A);
 
     // the ring starts zero-filled: rows of a ragged last tile that no copy ever wrote are
@@ -382,6 +455,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
             mbar_init(full + s, 1);
             mbar_init(empty + s, NW);
         }
+        mbar_init(xbar, 1);
+        ctl->sp[0] = ctl->sp[1] = ctl->sp[2] = ctl->sp[3] = 0.0;
         ctl->stop = 0;
         ctl->abort = 0;
         ctl->kc = 0;
@@ -402,13 +477,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
             volatile int *stopf = &ctl->stop;
             bool live = true;
             int mc = (int)(p.step0 % p.nblocks);
+            const uint32_t tile_bytes = (uint32_t)TR * (uint32_t)ld * (uint32_t)sizeof(T);
+            const uint32_t last_bytes = (uint32_t)(rows_c - (nt - 1) * TR) * (uint32_t)ld * (uint32_t)sizeof(T);
             for (int64_t step = 0; step < p.nsteps && live; ++step) {
                 const int m = p.order ? p.order[step] : mc;
                 if (++mc == p.nblocks) mc = 0;
-                const T *Ab = Aall + (int64_t)m * p.blk_stride + row0 * (int64_t)ld;
+                const unsigned char *Ab =
+                    reinterpret_cast<const unsigned char *>(Aall + (int64_t)m * p.blk_stride + row0 * (int64_t)ld);
+                const unsigned char *An = nullptr;   // slab of the next step, prefetched into L2
+                if (p.l2_ahead && step + 1 < p.nsteps) {
+                    const int mn = p.order ? p.order[step + 1] : mc;
+                    An = reinterpret_cast<const unsigned char *>(Aall + (int64_t)mn * p.blk_stride + row0 * (int64_t)ld);
+                }
                 for (int pass = 0; pass < 2 && live; ++pass) {
-                    const int ntl = pass == 0 ? nt : nreload;
-                    for (int t = 0; t < ntl; ++t) {
+                    for (int t = 0; t < nt; ++t) {
                         // pacing: a bounded number of bulk copies in flight
                         while (k - kd >= max_inflight) {
                             if (mbar_try_wait(full + dcur.slot, dcur.phase)) {
@@ -424,11 +506,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                             if (*stopf) { live = false; break; }
                         }
                         if (!live) break;
-                        const int rows_t = min(TR, rows_c - t * TR);
-                        const uint32_t bytes = (uint32_t)rows_t * (uint32_t)ld * (uint32_t)sizeof(T);
+                        const uint32_t bytes = t == nt - 1 ? last_bytes : tile_bytes;
                         mbar_expect_tx(full + cur.slot, bytes);
-                        tma_bulk_g2s(ring + (size_t)cur.slot * p.slot_bytes, Ab + (int64_t)t * TR * ld,
-                                     bytes, full + cur.slot);
+                        tma_bulk_g2s(ring + (size_t)cur.slot * p.slot_bytes, Ab + (size_t)t * tile_bytes, bytes,
+                                     full + cur.slot);
+                        // HBM runs one block ahead of the passes: while this step re-streams its
+                        // slab for pass 2 (L2 hits), pull the slab of the next step into L2
+                        if (pass == 1 - p.l2_pass && An) tma_prefetch_l2(An + (size_t)t * tile_bytes, bytes);
                         if (p.ttrace && t < 16)
                             p.ttrace[((size_t)c * p.nsteps + step) * NTTRACE + 64 + pass * 16 + t] = globaltimer_ns();
                         cur.advance(S);
@@ -456,7 +540,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
         bool have_prev = false;
         int m_prev = 0;
         int64_t step_prev = -1;
-        double sp_rq = 0, sp_qq = 0, sp_l1 = 0, sp_err = 0;  // thread 0 only
+        uint32_t xphase = 0;                                  // parity of the next exchange fetch
         double dprev = 0, xprev = 0;                          // column threads
         int64_t prev_idx = -1;
         long long block_cnt = p.state[2];
@@ -464,18 +548,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
         int stopped = 0, aborted = 0;
         int64_t steps_done = 0;
         const unsigned long long t_start = globaltimer_ns();
-        const int cs = p.cs, wpr = p.wpr, nrg = p.nrg;
+        const int cs = p.cs, nrg = p.nrg;
         const double mu = p.mu;
         const uint32_t tag0 = p.tag_base;
-        const ulonglong2 *inbox = p.gLL + (size_t)c * G * cs * WPC;
-        Waiter waiter{p.abort_flag, &ctl->abort, p.wait_limit_ns, 0u, 0ull};
+        const ulonglong2 *inbox = p.gLL + (size_t)c * G * p.mw;
+        Waiter waiter{p.abort_flag, &ctl->abort, p.wait_limit_ns, 0u, 0ull, p.state + 4, 0};
         unsigned long long *trace =
             (p.trace != nullptr && tid == 0) ? p.trace + (size_t)c * p.nsteps * NTRACE : nullptr;
         unsigned long long *ttrace =
             (p.ttrace != nullptr && tid == 0) ? p.ttrace + (size_t)c * p.nsteps * NTTRACE : nullptr;
         int mc = (int)(p.step0 % p.nblocks);
 
-        // pass-1 mapping: thread = (column group cg0 [+k*NTC], row-quad group rg of nrg)
+        // pass-1 mapping: thread = (column group cg0 [+k*NTC], row group rg of nrg)
         int cg0, rg;
         bool p1_active;
         if (CPT == 1) {
@@ -487,12 +571,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
             cg0 = tid;
             rg = 0;
         }
-        // pass-2 mapping: warp = (row rr0 [+rstep], column part); lane strides column groups
-        const int part = (wpr > 1) ? (wid % wpr) : 0;
-        const int rr0 = (wpr > 1) ? (wid / wpr) : wid;
-        const int rstep = (wpr > 1) ? TR : NW;
-        const int cstride = 32 * wpr;
-        const int cgl0 = lane + 32 * part;
+        // pass-2 mapping: warp = rows wid, wid+NW, .. of a tile; lane = column groups lane+32k
+        const int dk_n = (ncg + 31) >> 5;
         // stage-2 mapping: thread jl < cs owns column j0+jl of every block
         const int j0 = c * cs;
         const int jcol = j0 + tid;
@@ -512,7 +592,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
             // prox operands of my column: issued now, consumed after the gather
             const int64_t idx = (int64_t)m * ld + jcol;
             double xj = 0.0, dj = 0.0, drj = 0.0;
-            int keep_slot0 = 0;                 // ring slot of the first kept tile
+            // the slot of the last pass-1 tile is held back as the landing area of the two
+            // exchange fetches and handed to the producer only before pass 2 (slot 0 is idle
+            // when this CTA has no rows or in the closing iteration)
+            int hold_slot = 0;
             if (!drain) {
                 if (has_col) {
                     dj = p.d[idx];
@@ -521,11 +604,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                 }
 
                 // ---------------- pass 1: partial (A_m^T r, A_m^T q) over the slab ------
-                T ar[CPT][V], aq[CPT][V];
+                Acc ar[CPT], aq[CPT];
 #pragma unroll
-                for (int k = 0; k < CPT; ++k)
-#pragma unroll
-                    for (int e = 0; e < V; ++e) { ar[k][e] = (T)0; aq[k][e] = (T)0; }
+                for (int k = 0; k < CPT; ++k) { OP::zero(ar[k]); OP::zero(aq[k]); }
 
 #pragma unroll 1
                 for (int t = 0; t < nt; ++t, ++kc) {
@@ -553,8 +634,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                                             v[i] = *reinterpret_cast<const VecT *>(trow + (size_t)i * ld + k * NTC * V);
 #pragma unroll
                                         for (int i = 0; i < 4; ++i) {
-                                            vfma(ar[k], v[i], rv[i]);
-                                            vfma(aq[k], v[i], qv[i]);
+                                            OP::axpy(ar[k], v[i], rv[i]);
+                                            OP::axpy(aq[k], v[i], qv[i]);
                                         }
                                     }
                                 }
@@ -568,15 +649,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                                 for (int k = 0; k < CPT; ++k) {
                                     if (CPT == 1 || cg0 + k * NTC < ncg) {
                                         const VecT v = *reinterpret_cast<const VecT *>(trow + k * NTC * V);
-                                        vfma(ar[k], v, rv);
-                                        vfma(aq[k], v, qv);
+                                        OP::axpy(ar[k], v, rv);
+                                        OP::axpy(aq[k], v, qv);
                                     }
                                 }
                             }
                         }
                     }
-                    if (t == nreload) keep_slot0 = cur.slot;
-                    if (t < nreload) {              // not kept: hand the slot back to the producer
+                    if (t == nt - 1) {
+                        hold_slot = cur.slot;
+                    } else {                        // hand the slot back to the producer
                         __syncwarp();
                         if (lane == 0) mbar_arrive(empty + cur.slot);
                     }
@@ -585,24 +667,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                 }
                 if (trace) trace[step * NTRACE + 1] = globaltimer_ns() - t_start;
 
-                // combine the row groups of this CTA through shared memory and write the partial
-                // gradient into the readers' inboxes, one column per thread: the cs columns a
-                // reader owns are one contiguous message, so a warp stores whole 128-byte lines
+                // combine the row groups of this CTA through shared memory
                 if (p1_active) {
 #pragma unroll
                     for (int k = 0; k < CPT; ++k) {
                         const int cg = cg0 + k * NTC;
                         if (CPT == 1 || cg < ncg) {
-                            *reinterpret_cast<VecT *>(redT + (size_t)(rg * 2 + 0) * ld + cg * V) = vpack(ar[k]);
-                            *reinterpret_cast<VecT *>(redT + (size_t)(rg * 2 + 1) * ld + cg * V) = vpack(aq[k]);
+                            *reinterpret_cast<VecT *>(redT + (size_t)(rg * 2 + 0) * ld + cg * V) = OP::pack(ar[k]);
+                            *reinterpret_cast<VecT *>(redT + (size_t)(rg * 2 + 1) * ld + cg * V) = OP::pack(aq[k]);
                         }
                     }
                 }
-                cbar();
+            }
+            cbar();
+            // ---------------- publish: one message of MW words per reader -------------------
+            // [0..3] my line-search scalars of the pending step, [4..] the partial gradient of
+            // the cs columns that reader owns (one column per thread: a warp stores whole
+            // 128-byte lines), then padding up to the odd message length
+            {
+                const int MW = p.mw;
+                ulonglong2 *out = p.gLL + (size_t)c * MW;            // + reader * G * MW
 #pragma unroll 1
                 for (int j = tid; j < G * cs; j += NTC) {
                     T sr = (T)0, sq = (T)0;
-                    if (j < ld) {
+                    if (j < ld && !drain) {
 #pragma unroll 1
                         for (int g2 = 0; g2 < nrg; ++g2) {
                             sr += redT[(size_t)(g2 * 2 + 0) * ld + j];
@@ -611,78 +699,87 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                     }
                     const int rd = j >> p.cs_shift;
                     const int jj = j & (cs - 1);
-                    LL::put(p.gLL + (((size_t)rd * G + c) * cs + jj) * WPC, sr, sq, tag);
+                    LL::put(out + (size_t)rd * G * MW + 4 + jj * WPC, sr, sq, tag);
                 }
-            }
-            if (tid == 0) {
-                ll_st_dbl(p.sLL + (size_t)c * 4 + 0, sp_rq, tag);
-                ll_st_dbl(p.sLL + (size_t)c * 4 + 1, sp_qq, tag);
-                ll_st_dbl(p.sLL + (size_t)c * 4 + 2, sp_l1, tag);
-                ll_st_dbl(p.sLL + (size_t)c * 4 + 3, sp_err, tag);
+                const int sw = MW - cs * WPC;                          // scalars + padding: 4 or 5
+#pragma unroll 1
+                for (int e2 = tid; e2 < G * 8; e2 += NTC) {
+                    const int rd = e2 >> 3, k = e2 & 7;
+                    if (k < 4) ll_st_dbl(out + (size_t)rd * G * MW + k, ctl->sp[k], tag);
+                    else if (k < sw) ll_st(out + (size_t)rd * G * MW + MW - 1 - (k - 4), ll_pack(0u, tag), ll_pack(0u, tag));
+                }
             }
             if (trace && !drain) trace[step * NTRACE + 2] = globaltimer_ns() - t_start;
 
             // ---------------- gather -------------------------------------------------------
-            // (1) every thread polls a few words of this CTA's contiguous inbox (G*cs columns
-            // words, then the 4*G line-search scalars) until their tags match and drops the
-            // payloads in shared memory; (2) warp vc sums "virtual column" vc over the G sources
-            // in a fixed order (vc < 4: scalar vc of the pending step, else my column vc-4)
+            // My inbox (G messages, contiguous) is fetched by one bulk copy into the held slot;
+            // every thread checks the tags of a few words, a thread that finds one missing polls
+            // that word in L2 and the fetch is repeated.  Then warp vc sums "virtual column" vc
+            // (vc < 4: scalar vc, else my column vc-4) over the sources, lanes = sources, in a
+            // fixed order.  Inboxes larger than a slot are processed in groups of p.gc sources.
             {
-                const int nin = G * cs * WPC;
-                const int ntot = nin + 4 * G;
+                const int MW = p.mw;
+                ulonglong2 *stage = reinterpret_cast<ulonglong2 *>(ring + (size_t)hold_slot * p.slot_bytes);
+                const int nvc = 4 + cs;
 #pragma unroll 1
-                for (int e0 = (drain ? nin : 0) + tid; e0 < ntot; e0 += 4 * NTC) {
-                    ulonglong2 v[4];
-                    unsigned pend = 0;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (e0 + i * NTC < ntot) pend |= 1u << i;
-                    waiter.begin();
+                for (int g0 = 0; g0 < G; g0 += p.gc) {
+                    const int gn = min(p.gc, G - g0);
+                    const ulonglong2 *srcw = inbox + (size_t)g0 * MW;
+                    const int nwords = gn * MW;
                     for (;;) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int e = e0 + i * NTC;
-                            if (pend & (1u << i)) v[i] = ll_ld(e < nin ? inbox + e : p.sLL + (e - nin));
+                        if (tid == 0) {
+                            mbar_expect_tx(xbar, (uint32_t)nwords * 16u);
+                            tma_bulk_g2s(stage, srcw, (uint32_t)nwords * 16u, xbar);
                         }
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if ((pend & (1u << i)) && ll_ok(v[i], tag)) pend &= ~(1u << i);
-                        if (pend == 0 || (p.dbg & 1)) break;
-                        if (!waiter.again()) break;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int e = e0 + i * NTC;
-                        if (e < ntot) stage[e] = make_uint2((uint32_t)v[i].x, (uint32_t)v[i].y);
-                    }
-                }
-                cbar();
-                const int nvc = drain ? 4 : 4 + cs;
+                        mbar_wait(xbar, xphase);
+                        xphase ^= 1u;
+                        int bad = -1;
 #pragma unroll 1
-                for (int vc = wid; vc < nvc; vc += NW) {
-                    double a = 0.0, b = 0.0;
+                        for (int e = tid; e < nwords; e += NTC)
+                            if (!ll_ok(stage[e], tag)) { bad = e; break; }
+                        if (!cbar_or(bad >= 0) || (p.dbg & 1)) break;
+                        if (bad >= 0) {
+                            waiter.begin(((long long)step << 32) | ((long long)(g0 * MW + bad) & 0xffffffff));
+                            while (!ll_ok(ll_ld(srcw + bad), tag)) {
+                                if (!waiter.again()) break;
+                            }
+                        }
+                        if (cbar_or(*(volatile int *)&ctl->abort != 0)) break;
+                    }
 #pragma unroll 1
-                    for (int pp = lane; pp < G; pp += 32) {
-                        if (vc < 4) {
-                            const double sv = *reinterpret_cast<const double *>(stage + nin + pp * 4 + vc);
-                            if (vc == 3) a = fmax(a, sv); else a += sv;
-                        } else if (WPC == 1) {
-                            const uint2 w2 = stage[pp * cs + (vc - 4)];
-                            a += (double)__uint_as_float(w2.x);
-                            b += (double)__uint_as_float(w2.y);
+                    for (int vc = wid; vc < nvc; vc += NW) {
+                        double a = 0.0, b = 0.0;
+                        const int wi = vc < 4 ? vc : 4 + (vc - 4) * WPC;
+#pragma unroll 1
+                        for (int pp = lane; pp < gn; pp += 32) {
+                            const ulonglong2 w0 = stage[pp * MW + wi];
+                            if (vc < 4) {
+                                const double sv = ll_dbl(w0);
+                                if (vc == 3) a = fmax(a, sv); else a += sv;
+                            } else if (WPC == 1) {
+                                a += (double)__uint_as_float((uint32_t)w0.x);
+                                b += (double)__uint_as_float((uint32_t)w0.y);
+                            } else {
+                                a += ll_dbl(w0);
+                                b += ll_dbl(stage[pp * MW + wi + 1]);
+                            }
+                        }
+                        if (vc == 3) {
+                            a = warp_max(a);
                         } else {
-                            const double *w2 = reinterpret_cast<const double *>(stage + (pp * cs + (vc - 4)) * 2);
-                            a += w2[0];
-                            b += w2[1];
+                            a = warp_sum(a);
+                            b = warp_sum(b);
+                        }
+                        if (lane == 0) {
+                            if (g0 > 0) {
+                                const double2 o = colsum[vc];
+                                a = vc == 3 ? fmax(a, o.x) : a + o.x;
+                                b += o.y;
+                            }
+                            colsum[vc] = make_double2(a, b);
                         }
                     }
-                    if (vc == 3) {
-                        a = warp_max(a);
-                    } else {
-                        a = warp_sum(a);
-                        b = warp_sum(b);
-                    }
-                    if (lane == 0) colsum[vc] = make_double2(a, b);
+                    if (g0 + p.gc < G) cbar();     // the next group overwrites the landing area
                 }
             }
             cbar();
@@ -740,18 +837,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                     es[tid] = my_err;
                 }
             }
+            // A CTA that owns no column publishes an acknowledgement word instead.  Nobody starts
+            // pass 2 before every word of this fetch is there, i.e. before EVERY CTA has finished
+            // its gather -- which is what allows a writer to overwrite inbox words next step.
+            if (!drain && tid == 0 && j0 >= ld) ll_st(p.dLL + ld + (c - p.nown), ll_pack(0u, tag), ll_pack(0u, tag));
             if (trace && !drain) trace[step * NTRACE + 6] = globaltimer_ns() - t_start;
 
             // ---------------- the step D from all slice owners -------------------------
             if (!drain) {
+                ulonglong2 *stage = reinterpret_cast<ulonglong2 *>(ring + (size_t)hold_slot * p.slot_bytes);
+                const int dtot = ld + (G - p.nown);        // D words + acknowledgements
 #pragma unroll 1
-                for (int j = tid; j < ld; j += NTC) {
-                    T dv;
-                    waiter.begin();
-                    while (!LL::dtry(p.dLL, j, tag, dv) && !(p.dbg & 1)) {
-                        if (!waiter.again()) break;
+                for (int w0 = 0; w0 < dtot; w0 += p.dchunk) {
+                    const int nwords = min(p.dchunk, dtot - w0);
+                    const ulonglong2 *srcw = p.dLL + w0;
+                    if (w0 > 0) cbar();            // the previous chunk has been decoded
+                    for (;;) {
+                        if (tid == 0) {
+                            mbar_expect_tx(xbar, (uint32_t)nwords * 16u);
+                            tma_bulk_g2s(stage, srcw, (uint32_t)nwords * 16u, xbar);
+                        }
+                        mbar_wait(xbar, xphase);
+                        xphase ^= 1u;
+                        int bad = -1;
+#pragma unroll 1
+                        for (int e = tid; e < nwords; e += NTC)
+                            if (!ll_ok(stage[e], tag)) { bad = e; break; }
+                        if (!cbar_or(bad >= 0) || (p.dbg & 1)) break;
+                        if (bad >= 0) {
+                            waiter.begin(((long long)step << 32) | (1LL << 31) | (long long)(w0 + bad));
+                            while (!ll_ok(ll_ld(srcw + bad), tag)) {
+                                if (!waiter.again()) break;
+                            }
+                        }
+                        if (cbar_or(*(volatile int *)&ctl->abort != 0)) break;
                     }
-                    delta_s[j] = dv;
+#pragma unroll 1
+                    for (int e = tid; e < nwords; e += NTC)
+                        if (w0 + e < ld) delta_s[w0 + e] = LL::dval(stage[e]);
                 }
             }
             cbar();
@@ -774,69 +897,74 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                 }
             }
             if (drain) break;
+            if (nt > 0 && lane == 0) mbar_arrive(empty + hold_slot);   // the landing area goes back
             if (tid == 0) {
                 double a = 0.0, e = 0.0;
                 const int ncol = min(cs, max(0, ld - j0));
 #pragma unroll 1
                 for (int i = 0; i < ncol; ++i) { a += l1s[i]; e = fmax(e, es[i]); }
-                sp_l1 = a;
-                sp_err = e;
+                ctl->sp[2] = a;
+                ctl->sp[3] = e;
             }
             if (DK > 0) {
 #pragma unroll
                 for (int k = 0; k < DK; ++k) {
-                    const int cg = cgl0 + k * cstride;
+                    const int cg = lane + 32 * k;
                     dreg[k] = cg < ncg ? *reinterpret_cast<const VecT *>(delta_s + cg * V) : vzero(VecT());
                 }
             }
 
             // ---------------- pass 2: q = A_m D over the slab ---------------------------
-            // kept tiles first (already in the ring), then the re-streamed ones
             {
-                int ks = keep_slot0;
+                // one row of the tile against D: partial sum of this lane's column groups
+                auto row_dot = [&](const T *trow) -> T {
+                    Acc a0, a1;
+                    OP::zero(a0);
+                    OP::zero(a1);
+                    if (DK > 0) {
+#pragma unroll
+                        for (int k = 0; k < DK; k += 2) {
+                            if (k < dk_n) {
+                                const int cga = min(lane + 32 * k, ncg - 1);          // dreg is 0 past ncg
+                                const int cgb = min(lane + 32 * (k + 1), ncg - 1);
+                                const VecT va = *reinterpret_cast<const VecT *>(trow + cga * V);
+                                const VecT vb = *reinterpret_cast<const VecT *>(trow + cgb * V);
+                                OP::mac(a0, va, dreg[k]);
+                                OP::mac(a1, vb, dreg[k + 1 < DK ? k + 1 : k]);
+                            }
+                        }
+                    } else {
+#pragma unroll 2
+                        for (int cg = lane; cg < ncg; cg += 32) {
+                            const VecT v0 = *reinterpret_cast<const VecT *>(trow + cg * V);
+                            const VecT d0 = *reinterpret_cast<const VecT *>(delta_s + cg * V);
+                            OP::mac(a0, v0, d0);
+                        }
+                    }
+                    return OP::hsum(a0) + OP::hsum(a1);
+                };
 #pragma unroll 1
                 for (int t2 = 0; t2 < nt; ++t2) {
-                    const bool kept = t2 < keep;
-                    const int t = kept ? nreload + t2 : t2 - keep;
-                    int slot;
-                    if (kept) {
-                        slot = ks;
-                        if (++ks == S) ks = 0;
-                    } else {
-                        mbar_wait(full + cur.slot, cur.phase);
-                        slot = cur.slot;
-                        cur.advance(S);
-                        ++kc;
-                    }
+                    const int t = t2;
+                    mbar_wait(full + cur.slot, cur.phase);
+                    const int slot = cur.slot;
+                    cur.advance(S);
+                    ++kc;
                     if (ttrace && t2 < 16) ttrace[step * NTTRACE + 32 + t2] = globaltimer_ns();
                     const T *tile = reinterpret_cast<const T *>(ring + (size_t)slot * p.slot_bytes);
                     const int rows_t = min(TR, rows_c - t * TR);
                     if (!(p.dbg & 4)) {
+                        int rr = wid;
 #pragma unroll 1
-                        for (int rr = rr0; rr < rows_t; rr += rstep) {
-                            const T *trow = tile + (size_t)rr * ld;
-                            T a0 = (T)0, a1 = (T)0;
-                            if (DK > 0) {
-                                VecT v[DK > 0 ? DK : 1];
-#pragma unroll
-                                for (int k = 0; k < DK; ++k) {
-                                    const int cg = min(cgl0 + k * cstride, ncg - 1);   // dreg is 0 past ncg
-                                    v[k] = *reinterpret_cast<const VecT *>(trow + cg * V);
-                                }
-#pragma unroll
-                                for (int k = 0; k < DK; ++k) {
-                                    if (k & 1) a1 += vdot(v[k], dreg[k]); else a0 += vdot(v[k], dreg[k]);
-                                }
-                            } else {
-#pragma unroll 2
-                                for (int cg = cgl0; cg < ncg; cg += cstride) {
-                                    const VecT v0 = *reinterpret_cast<const VecT *>(trow + cg * V);
-                                    const VecT d0 = *reinterpret_cast<const VecT *>(delta_s + cg * V);
-                                    a0 += vdot(v0, d0);
-                                }
-                            }
-                            const T qv = warp_sum(a0 + a1);
-                            if (lane == 0) qpart[(size_t)(t * TR + rr) * wpr + part] = (double)qv;
+                        for (; rr + NW < rows_t; rr += 2 * NW) {      // two rows per trip
+                            const T qa = row_dot(tile + (size_t)rr * ld);
+                            const T qb = row_dot(tile + (size_t)(rr + NW) * ld);
+                            const T qs = warp_sum_pair(qa, qb, lane);
+                            if ((lane & 15) == 0) qpart[t * TR + rr + (lane >> 4) * NW] = (double)qs;
+                        }
+                        if (rr < rows_t) {
+                            const T qs = warp_sum(row_dot(tile + (size_t)rr * ld));
+                            if (lane == 0) qpart[t * TR + rr] = (double)qs;
                         }
                     }
                     __syncwarp();
@@ -850,8 +978,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                 double trq = 0.0, tqq = 0.0;
 #pragma unroll 1
                 for (int i = tid; i < rows_c; i += NTC) {
-                    double q = 0.0;
-                    for (int pt = 0; pt < wpr; ++pt) q += qpart[(size_t)i * wpr + pt];
+                    const double q = qpart[i];
                     q_loc[i] = q;
                     qT[i] = (T)q;
                     trq += r_loc[i] * q;                                     // lasso.py:129
@@ -864,8 +991,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                 if (wid == 0) {
                     const double a = warp_sum(lane < NW ? lsred[lane] : 0.0);
                     const double b = warp_sum(lane < NW ? lsred[NW + lane] : 0.0);
-                    sp_rq = a;
-                    sp_qq = b;
+                    if (lane == 0) { ctl->sp[0] = a; ctl->sp[1] = b; }
                 }
             }
             have_prev = true;
@@ -1029,8 +1155,7 @@ struct b200l_ctx {
     double *vin, *vout, *part;
     int part_chunks;
     // cross-CTA exchange buffers of the fused kernel (LL words, see above)
-    ulonglong2 *gLL, *sLL;
-    void *dLL;
+    ulonglong2 *gLL, *dLL;
     size_t gLL_bytes;
     int *abort_flag;
     uint32_t tag_base;            // tags already used by earlier launches
@@ -1047,7 +1172,7 @@ struct b200l_ctx {
     int32_t slot_target, keep_tiles, max_inflight, dbg;
     // cached geometry
     RunParams geo;
-    int grid, smem_bytes, cpt, dk, nt_max;
+    int grid, smem_bytes, cpt, nt_max;
     unsigned long long wait_limit_ns;
     int geo_valid;
 };
@@ -1122,7 +1247,7 @@ extern "C" int b200l_ctx_create(b200l_ctx **out, int dtype, int layout, int64_t 
     }
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = (int)prop.sharedMemPerBlockOptin;
-    c->slot_target = 32768;
+    c->slot_target = 65536;
     c->keep_tiles = -1;
     c->max_inflight = 0;
     c->wait_limit_ns = 5000000000ULL;
@@ -1141,8 +1266,7 @@ extern "C" int b200l_ctx_create(b200l_ctx **out, int dtype, int layout, int64_t 
     ALLOC(c->vin, vmax * 8);
     ALLOC(c->vout, vmax * 8);
     ALLOC(c->part, (int64_t)c->part_chunks * part_cols * 8);
-    ALLOC(c->sLL, (int64_t)GMAX * 4 * 16);
-    ALLOC(c->dLL, c->xld * 16);
+    ALLOC(c->dLL, (c->xld + GMAX) * 16);
     ALLOC(c->abort_flag, 64);
     ALLOC(c->gamma_state, 8);
     ALLOC(c->objbuf, 64);
@@ -1155,8 +1279,7 @@ extern "C" int b200l_ctx_create(b200l_ctx **out, int dtype, int layout, int64_t 
     CK(cudaMemset(c->b, 0, N * 8));
     CK(cudaMemset(c->gamma_state, 0, 8));
     CK(cudaMemset(c->state, 0, 64));
-    CK(cudaMemset(c->sLL, 0, (size_t)GMAX * 4 * 16));
-    CK(cudaMemset(c->dLL, 0, (size_t)c->xld * 16));
+    CK(cudaMemset(c->dLL, 0, (size_t)(c->xld + GMAX) * 16));
     CK(cudaMemset(c->abort_flag, 0, 64));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
@@ -1169,7 +1292,7 @@ extern "C" int b200l_ctx_destroy(b200l_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->x, c->d, c->drec, c->dsum, c->r, c->b, c->vin, c->vout, c->part, c->gLL,
-                    c->sLL, c->dLL, c->abort_flag, c->gamma_state, c->objbuf, c->state, c->err_hist,
+                    c->dLL, c->abort_flag, c->gamma_state, c->objbuf, c->state, c->err_hist,
                     c->time_hist, c->trace, c->ttrace, c->order};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -1399,7 +1522,7 @@ extern "C" int b200l_objective(b200l_ctx *c, double mu, double *value) {
 extern "C" int b200l_set_tuning(b200l_ctx *c, int32_t slot_bytes_target, int32_t keep_tiles,
                                 int32_t max_inflight_tiles) {
     if (!c) return fail("ctx is NULL");
-    c->slot_target = slot_bytes_target > 0 ? slot_bytes_target : 32768;
+    c->slot_target = slot_bytes_target > 0 ? slot_bytes_target : 65536;
     c->keep_tiles = keep_tiles;
     c->max_inflight = max_inflight_tiles;
     c->geo_valid = 0;
@@ -1409,25 +1532,18 @@ extern "C" int b200l_set_tuning(b200l_ctx *c, int32_t slot_bytes_target, int32_t
 typedef void (*fused_fn)(const RunParams);
 
 template <typename T>
-static fused_fn pick_kernel(int cpt, int dk) {
-    if (dk == 4) {
-        switch (cpt) {
-            case 1: return lasso_fused_rowmajor<T, 1, 4>;
-            case 2: return lasso_fused_rowmajor<T, 2, 4>;
-            case 4: return lasso_fused_rowmajor<T, 4, 4>;
-            default: return nullptr;
-        }
-    }
+static fused_fn pick_kernel(int cpt) {
     switch (cpt) {
-        case 1: return lasso_fused_rowmajor<T, 1, 0>;
-        case 2: return lasso_fused_rowmajor<T, 2, 0>;
-        case 4: return lasso_fused_rowmajor<T, 4, 0>;
+        case 1: return lasso_fused_rowmajor<T, 1>;
+        case 2: return lasso_fused_rowmajor<T, 2>;
+        case 4: return lasso_fused_rowmajor<T, 4>;
+        case 8: return lasso_fused_rowmajor<T, 8>;
         default: return nullptr;
     }
 }
 
 static fused_fn ctx_kernel(const b200l_ctx *c) {
-    return c->dtype == B200L_F32 ? pick_kernel<float>(c->cpt, c->dk) : pick_kernel<double>(c->cpt, c->dk);
+    return c->dtype == B200L_F32 ? pick_kernel<float>(c->cpt) : pick_kernel<double>(c->cpt);
 }
 
 static int plan_geometry(b200l_ctx *c) {
@@ -1447,15 +1563,12 @@ static int plan_geometry(b200l_ctx *c) {
     const int ncg = ld / V;
     int cpt = 1;
     while (cpt * NTC < ncg) cpt *= 2;
-    if (cpt > 4) return fail("internal: cpt=%d", cpt);
+    if (cpt > 8) return fail("internal: cpt=%d", cpt);
     const int nrg = cpt == 1 ? std::max(1, NTC / ncg) : 1;
-    int TR = 1;
-    while ((int64_t)TR * 2 * rowbytes <= c->slot_target && TR * 2 <= 64 &&
-           TR < std::max(1, rows_max))
-        TR *= 2;
-    const int wpr = TR >= NW ? 1 : NW / TR;
-    const int dk_need = (ncg + 32 * wpr - 1) / (32 * wpr);
-    const int dk = dk_need <= 4 ? 4 : 0;
+    // rows per tile: as many as fit the slot target, whole quads when possible, at most 64
+    int TR = (int)std::min<int64_t>(64, std::max<int64_t>(1, c->slot_target / rowbytes));
+    TR = std::min(TR, (int)round_up(std::max(rows_max, 1), 4));
+    if (TR >= 4) TR &= ~3;
     // columns of every block owned by one CTA: a power of two (shift/mask addressing)
     int cs = 1, cs_shift = 0;
     while (cs * G < ld) { cs *= 2; ++cs_shift; }
@@ -1477,14 +1590,12 @@ static int plan_geometry(b200l_ctx *c) {
         const int o_redT = take(nrg * 2 * ld * es);
         const int o_delta = o_redT;
         const int o_colsum = take((4 + cs) * 16);                 // gathered scalars + columns
-        const int o_stage = take((G * cs * (es / 4) + 4 * G) * 8); // payloads of the polled words
         const int o_small = take((2 * MAX_CS + 2 * NW) * 8);      // l1s, es, lsred
-        const int o_qpart = take(rows_pad * wpr * 8);
+        const int o_qpart = take(rows_pad * 8);
         if (out) {
             out->off_bar = o_bar; out->off_ctl = o_ctl; out->off_rloc = o_rloc; out->off_qloc = o_qloc;
             out->off_rT = o_rT; out->off_qT = o_qT; out->off_delta = o_delta; out->off_redT = o_redT;
-            out->off_colsum = o_colsum; out->off_stage = o_stage; out->off_small = o_small;
-            out->off_qpart = o_qpart;
+            out->off_colsum = o_colsum; out->off_small = o_small; out->off_qpart = o_qpart;
         }
     };
     // the ring goes first (offset 0); sized after the fixed part is known
@@ -1493,7 +1604,7 @@ static int plan_geometry(b200l_ctx *c) {
     const int fixed = off;
     const int avail = c->smem_optin - fixed;
     int S = avail / slot_bytes;
-    if (S > 64) S = 64;
+    if (S > 60) S = 60;
     if (S < 2)
         return fail("shared memory too small for the fused kernel: fixed=%d slot=%d optin=%d (N/SM=%d rows, "
                     "w=%d)", fixed, slot_bytes, c->smem_optin, rows_max, c->w);
@@ -1505,17 +1616,31 @@ static int plan_geometry(b200l_ctx *c) {
     c->smem_bytes = off;
     c->grid = G;
     c->cpt = cpt;
-    c->dk = dk;
     c->nt_max = nt_max;
-    int keep = c->keep_tiles >= 0 ? c->keep_tiles : 0;
-    keep = std::min(keep, std::min(S, nt_max));
-    g.TR = TR; g.S = S; g.slot_bytes = slot_bytes; g.cs = cs; g.cs_shift = cs_shift; g.wpr = wpr;
+    // exchange geometry: message = 4 scalars + cs columns, padded to an odd word count (bank
+    // spread of the per-source reads); both exchange fetches land in one ring slot
+    const int wpc = es / 4;
+    const int mw = (4 + cs * wpc) | 1;
+    const int slot_words = slot_bytes / 16;
+    int gc = G;
+    if (G * mw > slot_words) {
+        gc = slot_words / mw;
+        if (gc >= 32) gc &= ~31;
+        if (gc < 1) return fail("internal: a ring slot (%d B) cannot hold one exchange message (%d B)",
+                                slot_bytes, mw * 16);
+    }
+    const int nown = (ld + cs - 1) / cs;                 // CTAs that own at least one column
+    const int dchunk = std::min(ld + (G - nown), slot_words);
+    g.TR = TR; g.S = S; g.slot_bytes = slot_bytes; g.cs = cs; g.cs_shift = cs_shift;
     g.ring_bytes = S * slot_bytes;
-    g.nrg = nrg; g.ncg = ncg; g.rows_pad = rows_pad; g.keep = keep;
+    g.nrg = nrg; g.ncg = ncg; g.rows_pad = rows_pad;
+    g.mw = mw; g.gc = gc; g.dchunk = dchunk; g.nown = nown;
     g.inflight = c->max_inflight > 0 ? std::min(c->max_inflight, S) : S;
+    g.l2_ahead = (c->dbg & 8) ? 0 : 1;
+    g.l2_pass = (c->dbg & 16) ? 1 : 0;
 
     // inboxes of the partial block gradients: [G readers][G writers][cs][WPC] LL words
-    const size_t need = (size_t)G * G * cs * (es / 4) * 16;
+    const size_t need = (size_t)G * G * mw * 16;
     if (c->gLL_bytes < need) {
         if (c->gLL) CK(cudaFree(c->gLL));
         c->gLL = nullptr;
@@ -1525,7 +1650,7 @@ static int plan_geometry(b200l_ctx *c) {
     }
 
     fused_fn fn = ctx_kernel(c);
-    if (!fn) return fail("internal: no kernel for cpt=%d dk=%d", cpt, dk);
+    if (!fn) return fail("internal: no kernel for cpt=%d", cpt);
     CK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_bytes));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, NTHREADS, c->smem_bytes));
@@ -1583,8 +1708,7 @@ static int launch_fused(b200l_ctx *c, const int32_t *order_host, int64_t nsteps,
     // tags tag_base+1 .. tag_base+nsteps+1 are consumed by this launch; never reuse one
     if ((uint64_t)c->tag_base + (uint64_t)nsteps + 2 >= 0xffffffffULL) {
         CK(cudaMemsetAsync(c->gLL, 0, c->gLL_bytes, c->stream));
-        CK(cudaMemsetAsync(c->sLL, 0, (size_t)GMAX * 4 * 16, c->stream));
-        CK(cudaMemsetAsync(c->dLL, 0, (size_t)c->xld * 16, c->stream));
+        CK(cudaMemsetAsync(c->dLL, 0, (size_t)(c->xld + GMAX) * 16, c->stream));
         c->tag_base = 0;
     }
 
@@ -1596,7 +1720,7 @@ static int launch_fused(b200l_ctx *c, const int32_t *order_host, int64_t nsteps,
     p.ld = (int32_t)c->ld;
     p.nblocks = c->nblocks;
     p.x = c->x; p.d = c->d; p.drec = c->drec; p.r = c->r;
-    p.gLL = c->gLL; p.sLL = c->sLL; p.dLL = c->dLL; p.abort_flag = c->abort_flag;
+    p.gLL = c->gLL; p.dLL = c->dLL; p.abort_flag = c->abort_flag;
     p.order = order_host ? c->order : nullptr;
     p.nsteps = nsteps;
     p.step0 = c->step_counter;
@@ -1626,14 +1750,15 @@ static int launch_fused(b200l_ctx *c, const int32_t *order_host, int64_t nsteps,
 
 // reads back the launch status; fails when the kernel abandoned a cross-CTA wait
 static int finish_fused(b200l_ctx *c, int64_t *steps_done, int32_t *stopped, double *kernel_ms) {
-    long long st[4];
+    long long st[8];
     CK(cudaMemcpyAsync(st, c->state, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     if (st[3]) {
         CK(cudaMemsetAsync(c->abort_flag, 0, 64, c->stream));
         CK(cudaMemsetAsync(c->state, 0, 64, c->stream));
-        return fail("fused kernel aborted: a cross-CTA wait exceeded %.1f s (solver state is invalid; call "
-                    "b200l_reset)", (double)c->wait_limit_ns * 1e-9);
+        return fail("fused kernel aborted: a cross-CTA wait exceeded %.1f s (CTA %lld thread %lld step %lld %s word "
+                    "%lld; solver state is invalid; call b200l_reset)", (double)c->wait_limit_ns * 1e-9, st[4],
+                    st[5], st[6] >> 32, (st[6] & 0x80000000LL) ? "step-D" : "inbox", st[6] & 0x7fffffffLL);
     }
     if (steps_done) *steps_done = st[0];
     if (stopped) *stopped = (int32_t)st[1];
@@ -1726,5 +1851,6 @@ extern "C" int b200l_set_wait_limit(b200l_ctx *c, double seconds) {
 extern "C" int b200l_debug_flags(b200l_ctx *c, int32_t flags) {
     if (!c) return fail("ctx is NULL");
     c->dbg = flags;
+    c->geo_valid = 0;
     return 0;
 }
