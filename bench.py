@@ -250,8 +250,8 @@ def main_gpu(args):
     store, b, mu = make_device_instance(torch, device, N, K, BLOCK, cfg["den"], cfg["seed"] + rank,
                                         tdt, ld, layout)
     cal = Cal.from_device_blocks(store, N, K, BLOCK)
-    if args.slot_bytes or args.keep_tiles >= 0 or args.inflight:
-        cal.set_tuning(args.slot_bytes, args.keep_tiles, args.inflight)
+    if args.slot_bytes or args.inflight:
+        cal.set_tuning(args.slot_bytes, args.inflight)
     lib, ctx = cal._lib, cal.ctx
     d_ATA = cal.diag_ATA
     geo = cal.run_config()
@@ -373,7 +373,6 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-sweeps", type=int, default=5)
     ap.add_argument("--slot-bytes", type=int, default=0)
-    ap.add_argument("--keep-tiles", type=int, default=-1)
     ap.add_argument("--inflight", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

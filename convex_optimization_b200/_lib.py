@@ -76,7 +76,7 @@ PROTOTYPES = {
     "b200l_get_r": (_c_int, [_p, _pd]),
     "b200l_run": (_c_int, [_p, _pi32, _c_i64, _c_dbl, _c_dbl, _pd, _pd, _pi64, _pi32, _pd]),
     "b200l_run_config": (_c_int, [_p, _pi32, _pi32, _pi32, _pi32, _pi32, _pi32]),
-    "b200l_set_tuning": (_c_int, [_p, _c_i32, _c_i32, _c_i32]),
+    "b200l_set_tuning": (_c_int, [_p, _c_i32, _c_i32]),
     "b200l_run_traced": (_c_int, [_p, _c_i64, _c_dbl, ctypes.POINTER(ctypes.c_uint64),
                          ctypes.POINTER(ctypes.c_uint64), _pi32, _pd]),
     "b200l_set_wait_limit": (_c_int, [_p, _c_dbl]),

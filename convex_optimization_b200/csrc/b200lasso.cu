@@ -189,6 +189,11 @@ __device__ __forceinline__ bool cbar_or(bool pred) {
         : "memory");
     return out != 0;
 }
+// two adjacent words with one 256-bit store (whole 32-byte sectors; p 32-byte aligned)
+__device__ __forceinline__ void ll_st2(ulonglong2 *p, unsigned long long a, unsigned long long b,
+                                       unsigned long long c, unsigned long long d) {
+    asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
 __device__ __forceinline__ unsigned long long ll_pack(uint32_t payload, uint32_t tag) {
     return ((unsigned long long)tag << 32) | (unsigned long long)payload;
 }
@@ -219,6 +224,13 @@ template <> struct LLW<float> {
         ll_st(base + j, ll_pack(__float_as_uint(v), tag), ll_pack(0u, tag));
     }
     __device__ static __forceinline__ float dval(const ulonglong2 v) { return __uint_as_float((uint32_t)v.x); }
+    // the four columns of one column group: words p[0..3] = (g_r, g_q) pairs
+    __device__ static __forceinline__ void put_group(ulonglong2 *p, const float4 r, const float4 q, uint32_t tag) {
+        ll_st2(p, ll_pack(__float_as_uint(r.x), tag), ll_pack(__float_as_uint(q.x), tag),
+               ll_pack(__float_as_uint(r.y), tag), ll_pack(__float_as_uint(q.y), tag));
+        ll_st2(p + 2, ll_pack(__float_as_uint(r.z), tag), ll_pack(__float_as_uint(q.z), tag),
+               ll_pack(__float_as_uint(r.w), tag), ll_pack(__float_as_uint(q.w), tag));
+    }
 };
 template <> struct LLW<double> {
     static constexpr int WPC = 2;
@@ -234,6 +246,13 @@ template <> struct LLW<double> {
         ll_st_dbl(base + j, v, tag);
     }
     __device__ static __forceinline__ double dval(const ulonglong2 v) { return ll_dbl(v); }
+    // the two columns of one column group: words p[0..3] = g_r, g_q, g_r, g_q
+    __device__ static __forceinline__ void put_group(ulonglong2 *p, const double2 r, const double2 q, uint32_t tag) {
+        ll_st2(p, ll_pack((uint32_t)__double2loint(r.x), tag), ll_pack((uint32_t)__double2hiint(r.x), tag),
+               ll_pack((uint32_t)__double2loint(q.x), tag), ll_pack((uint32_t)__double2hiint(q.x), tag));
+        ll_st2(p + 2, ll_pack((uint32_t)__double2loint(r.y), tag), ll_pack((uint32_t)__double2hiint(r.y), tag),
+               ll_pack((uint32_t)__double2loint(q.y), tag), ll_pack((uint32_t)__double2hiint(q.y), tag));
+    }
 };
 
 constexpr int NTTRACE = 96;        // per-tile stamps: 6 groups of 16 (see b200lasso.h)
@@ -249,6 +268,7 @@ struct Ctl {
     unsigned long long kc, k_issued;
     int stop;
     int abort;
+    long long gate;                  // steps whose pass-2 copies the producer may issue
 };
 
 struct RunParams {
@@ -278,6 +298,8 @@ struct RunParams {
     unsigned long long wait_limit_ns;
     // geometry
     int32_t TR, S, slot_bytes, cs, cs_shift, nrg, ncg, rows_pad, inflight, l2_ahead, l2_pass;
+    int32_t direct_pub;       // partial gradients are published from registers (one row group)
+    int32_t gate_mode;        // 0: re-stream freely, 1/2/3: after inbox fetch issued / gather done / D fetch issued
     int32_t mw, gc, dchunk, nown;   // message words, sources per gather group, D words per fetch, owner CTAs
     // shared-memory offsets
     int32_t off_bar, off_ctl, off_rloc, off_qloc, off_rT, off_qT, off_delta, off_redT, off_colsum,
@@ -459,6 +481,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
         ctl->sp[0] = ctl->sp[1] = ctl->sp[2] = ctl->sp[3] = 0.0;
         ctl->stop = 0;
         ctl->abort = 0;
+        ctl->gate = 0;
         ctl->kc = 0;
         ctl->k_issued = 0;
         fence_mbar_init();
@@ -490,6 +513,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                     An = reinterpret_cast<const unsigned char *>(Aall + (int64_t)mn * p.blk_stride + row0 * (int64_t)ld);
                 }
                 for (int pass = 0; pass < 2 && live; ++pass) {
+                    // the re-stream for pass 2 is held back until the consumers have their
+                    // exchange fetch in flight: it would otherwise sit in front of it in the
+                    // TMA queue and on the L2 link
+                    if (pass == 1 && p.gate_mode) {
+                        while (*(volatile long long *)&ctl->gate <= step) {
+                            if (*stopf) { live = false; break; }
+                            __nanosleep(64);
+                        }
+                        if (!live) break;
+                    }
                     for (int t = 0; t < nt; ++t) {
                         // pacing: a bounded number of bulk copies in flight
                         while (k - kd >= max_inflight) {
@@ -667,8 +700,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                 }
                 if (trace) trace[step * NTRACE + 1] = globaltimer_ns() - t_start;
 
-                // combine the row groups of this CTA through shared memory
-                if (p1_active) {
+                // when every thread holds complete column sums (one row group) the partial
+                // gradient goes out straight from registers: the V columns of a column group
+                // are 4 adjacent words of one reader's message, two 256-bit stores
+                if (p.direct_pub) {
+                    if (p1_active) {
+#pragma unroll
+                        for (int k = 0; k < CPT; ++k) {
+                            const int cg = cg0 + k * NTC;
+                            if (CPT == 1 || cg < ncg) {
+                                const int j = cg * V;
+                                const int rd = j >> p.cs_shift;
+                                const int jj = j & (cs - 1);
+                                LL::put_group(p.gLL + ((size_t)rd * G + c) * p.mw + 4 + jj * WPC, OP::pack(ar[k]),
+                                              OP::pack(aq[k]), tag);
+                            }
+                        }
+                    }
+                } else if (p1_active) {
+                    // combine the row groups of this CTA through shared memory
 #pragma unroll
                     for (int k = 0; k < CPT; ++k) {
                         const int cg = cg0 + k * NTC;
@@ -683,30 +733,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
             // ---------------- publish: one message of MW words per reader -------------------
             // [0..3] my line-search scalars of the pending step, [4..] the partial gradient of
             // the cs columns that reader owns (one column per thread: a warp stores whole
-            // 128-byte lines), then padding up to the odd message length
+            // 128-byte lines), then padding up to the message length
             {
                 const int MW = p.mw;
                 ulonglong2 *out = p.gLL + (size_t)c * MW;            // + reader * G * MW
+                if (!p.direct_pub || drain) {
 #pragma unroll 1
-                for (int j = tid; j < G * cs; j += NTC) {
-                    T sr = (T)0, sq = (T)0;
-                    if (j < ld && !drain) {
+                    for (int j = tid; j < G * cs; j += NTC) {
+                        T sr = (T)0, sq = (T)0;
+                        if (j < ld && !drain) {
 #pragma unroll 1
-                        for (int g2 = 0; g2 < nrg; ++g2) {
-                            sr += redT[(size_t)(g2 * 2 + 0) * ld + j];
-                            sq += redT[(size_t)(g2 * 2 + 1) * ld + j];
+                            for (int g2 = 0; g2 < nrg; ++g2) {
+                                sr += redT[(size_t)(g2 * 2 + 0) * ld + j];
+                                sq += redT[(size_t)(g2 * 2 + 1) * ld + j];
+                            }
                         }
+                        const int rd = j >> p.cs_shift;
+                        const int jj = j & (cs - 1);
+                        LL::put(out + (size_t)rd * G * MW + 4 + jj * WPC, sr, sq, tag);
                     }
-                    const int rd = j >> p.cs_shift;
-                    const int jj = j & (cs - 1);
-                    LL::put(out + (size_t)rd * G * MW + 4 + jj * WPC, sr, sq, tag);
+                } else {
+                    // columns past ld (readers' padding columns) still have to carry the tag
+#pragma unroll 1
+                    for (int j = ncg * V + tid; j < G * cs; j += NTC) {
+                        const int rd = j >> p.cs_shift;
+                        const int jj = j & (cs - 1);
+                        LL::put(out + (size_t)rd * G * MW + 4 + jj * WPC, (T)0, (T)0, tag);
+                    }
                 }
-                const int sw = MW - cs * WPC;                          // scalars + padding: 4 or 5
+                const int npad = MW - 4 - cs * WPC;                     // 0..2 padding words
 #pragma unroll 1
                 for (int e2 = tid; e2 < G * 8; e2 += NTC) {
                     const int rd = e2 >> 3, k = e2 & 7;
                     if (k < 4) ll_st_dbl(out + (size_t)rd * G * MW + k, ctl->sp[k], tag);
-                    else if (k < sw) ll_st(out + (size_t)rd * G * MW + MW - 1 - (k - 4), ll_pack(0u, tag), ll_pack(0u, tag));
+                    else if (k - 4 < npad) ll_st(out + (size_t)rd * G * MW + MW - 1 - (k - 4), ll_pack(0u, tag), ll_pack(0u, tag));
                 }
             }
             if (trace && !drain) trace[step * NTRACE + 2] = globaltimer_ns() - t_start;
@@ -730,13 +790,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                         if (tid == 0) {
                             mbar_expect_tx(xbar, (uint32_t)nwords * 16u);
                             tma_bulk_g2s(stage, srcw, (uint32_t)nwords * 16u, xbar);
+                            if (p.gate_mode == 1) *(volatile long long *)&ctl->gate = step + 1;
                         }
                         mbar_wait(xbar, xphase);
                         xphase ^= 1u;
                         int bad = -1;
-#pragma unroll 1
+#pragma unroll 4
                         for (int e = tid; e < nwords; e += NTC)
-                            if (!ll_ok(stage[e], tag)) { bad = e; break; }
+                            if (!ll_ok(stage[e], tag)) bad = e;
                         if (!cbar_or(bad >= 0) || (p.dbg & 1)) break;
                         if (bad >= 0) {
                             waiter.begin(((long long)step << 32) | ((long long)(g0 * MW + bad) & 0xffffffff));
@@ -746,43 +807,66 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                         }
                         if (cbar_or(*(volatile int *)&ctl->abort != 0)) break;
                     }
+                    // two virtual columns per warp and trip, sources unrolled: the loads and the
+                    // four butterflies overlap instead of queueing behind one another
 #pragma unroll 1
-                    for (int vc = wid; vc < nvc; vc += NW) {
-                        double a = 0.0, b = 0.0;
-                        const int wi = vc < 4 ? vc : 4 + (vc - 4) * WPC;
-#pragma unroll 1
-                        for (int pp = lane; pp < gn; pp += 32) {
-                            const ulonglong2 w0 = stage[pp * MW + wi];
-                            if (vc < 4) {
-                                const double sv = ll_dbl(w0);
-                                if (vc == 3) a = fmax(a, sv); else a += sv;
-                            } else if (WPC == 1) {
-                                a += (double)__uint_as_float((uint32_t)w0.x);
-                                b += (double)__uint_as_float((uint32_t)w0.y);
-                            } else {
-                                a += ll_dbl(w0);
-                                b += ll_dbl(stage[pp * MW + wi + 1]);
+                    for (int vc0 = wid; vc0 < nvc; vc0 += 2 * NW) {
+                        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int vc = vc0 + h * NW;
+                            if (vc < nvc) {
+                                const int wi = vc < 4 ? vc : 4 + (vc - 4) * WPC;
+#pragma unroll
+                                for (int i = 0; i < PPL; ++i) {
+                                    const int pp = lane + 32 * i;
+                                    if (pp < gn) {
+                                        const ulonglong2 w0 = stage[pp * MW + wi];
+                                        if (vc < 4) {
+                                            const double sv = ll_dbl(w0);
+                                            acc[h][0] = vc == 3 ? fmax(acc[h][0], sv) : acc[h][0] + sv;
+                                        } else if (WPC == 1) {
+                                            acc[h][0] += (double)__uint_as_float((uint32_t)w0.x);
+                                            acc[h][1] += (double)__uint_as_float((uint32_t)w0.y);
+                                        } else {
+                                            acc[h][0] += ll_dbl(w0);
+                                            acc[h][1] += ll_dbl(stage[pp * MW + wi + 1]);
+                                        }
+                                    }
+                                }
                             }
                         }
-                        if (vc == 3) {
-                            a = warp_max(a);
-                        } else {
-                            a = warp_sum(a);
-                            b = warp_sum(b);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const double oa = __shfl_xor_sync(0xffffffffu, acc[h][0], o);
+                                const double ob = __shfl_xor_sync(0xffffffffu, acc[h][1], o);
+                                acc[h][0] = (vc0 + h * NW == 3) ? fmax(acc[h][0], oa) : acc[h][0] + oa;
+                                acc[h][1] += ob;
+                            }
                         }
                         if (lane == 0) {
-                            if (g0 > 0) {
-                                const double2 o = colsum[vc];
-                                a = vc == 3 ? fmax(a, o.x) : a + o.x;
-                                b += o.y;
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const int vc = vc0 + h * NW;
+                                if (vc < nvc) {
+                                    double a = acc[h][0], bq = acc[h][1];
+                                    if (g0 > 0) {
+                                        const double2 o = colsum[vc];
+                                        a = vc == 3 ? fmax(a, o.x) : a + o.x;
+                                        bq += o.y;
+                                    }
+                                    colsum[vc] = make_double2(a, bq);
+                                }
                             }
-                            colsum[vc] = make_double2(a, b);
                         }
                     }
                     if (g0 + p.gc < G) cbar();     // the next group overwrites the landing area
                 }
             }
             cbar();
+            if (tid == 0 && p.gate_mode == 2) *(volatile long long *)&ctl->gate = step + 1;
             if (trace && !drain) trace[step * NTRACE + 3] = trace[step * NTRACE + 4] = globaltimer_ns() - t_start;
 
             // ---------------- resolve the pending step: error, stop rule, gamma ---------
@@ -856,13 +940,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                         if (tid == 0) {
                             mbar_expect_tx(xbar, (uint32_t)nwords * 16u);
                             tma_bulk_g2s(stage, srcw, (uint32_t)nwords * 16u, xbar);
+                            if (p.gate_mode == 3) *(volatile long long *)&ctl->gate = step + 1;
                         }
                         mbar_wait(xbar, xphase);
                         xphase ^= 1u;
                         int bad = -1;
-#pragma unroll 1
+#pragma unroll 4
                         for (int e = tid; e < nwords; e += NTC)
-                            if (!ll_ok(stage[e], tag)) { bad = e; break; }
+                            if (!ll_ok(stage[e], tag)) bad = e;
                         if (!cbar_or(bad >= 0) || (p.dbg & 1)) break;
                         if (bad >= 0) {
                             waiter.begin(((long long)step << 32) | (1LL << 31) | (long long)(w0 + bad));
@@ -872,7 +957,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                         }
                         if (cbar_or(*(volatile int *)&ctl->abort != 0)) break;
                     }
-#pragma unroll 1
+#pragma unroll 4
                     for (int e = tid; e < nwords; e += NTC)
                         if (w0 + e < ld) delta_s[w0 + e] = LL::dval(stage[e]);
                 }
@@ -1169,7 +1254,7 @@ struct b200l_ctx {
     int have_problem;
     cudaEvent_t ev0, ev1;
     // tuning
-    int32_t slot_target, keep_tiles, max_inflight, dbg;
+    int32_t slot_target, max_inflight, dbg;
     // cached geometry
     RunParams geo;
     int grid, smem_bytes, cpt, nt_max;
@@ -1248,7 +1333,6 @@ extern "C" int b200l_ctx_create(b200l_ctx **out, int dtype, int layout, int64_t 
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = (int)prop.sharedMemPerBlockOptin;
     c->slot_target = 65536;
-    c->keep_tiles = -1;
     c->max_inflight = 0;
     c->wait_limit_ns = 5000000000ULL;
 
@@ -1519,11 +1603,9 @@ extern "C" int b200l_objective(b200l_ctx *c, double mu, double *value) {
 // ------------------------------------------------------------------------------------
 // fused launch
 // ------------------------------------------------------------------------------------
-extern "C" int b200l_set_tuning(b200l_ctx *c, int32_t slot_bytes_target, int32_t keep_tiles,
-                                int32_t max_inflight_tiles) {
+extern "C" int b200l_set_tuning(b200l_ctx *c, int32_t slot_bytes_target, int32_t max_inflight_tiles) {
     if (!c) return fail("ctx is NULL");
     c->slot_target = slot_bytes_target > 0 ? slot_bytes_target : 65536;
-    c->keep_tiles = keep_tiles;
     c->max_inflight = max_inflight_tiles;
     c->geo_valid = 0;
     return 0;
@@ -1589,7 +1671,7 @@ static int plan_geometry(b200l_ctx *c) {
         // partials (written after pass 1, read before the gather): two barriers apart
         const int o_redT = take(nrg * 2 * ld * es);
         const int o_delta = o_redT;
-        const int o_colsum = take((4 + cs) * 16);                 // gathered scalars + columns
+        const int o_colsum = take(2 * (4 + MAX_CS) * 16);         // gathered scalars + columns (+ group sums)
         const int o_small = take((2 * MAX_CS + 2 * NW) * 8);      // l1s, es, lsred
         const int o_qpart = take(rows_pad * 8);
         if (out) {
@@ -1620,7 +1702,10 @@ static int plan_geometry(b200l_ctx *c) {
     // exchange geometry: message = 4 scalars + cs columns, padded to an odd word count (bank
     // spread of the per-source reads); both exchange fetches land in one ring slot
     const int wpc = es / 4;
-    const int mw = (4 + cs * wpc) | 1;
+    // publishing from registers needs complete column sums per thread (one row group), a
+    // column group inside one message and 32-byte aligned messages (even word count)
+    const int direct = (nrg == 1 && cs * wpc >= 4 && !(c->dbg & 128)) ? 1 : 0;
+    const int mw = direct ? ((4 + cs * wpc + 1) & ~1) : ((4 + cs * wpc) | 1);
     const int slot_words = slot_bytes / 16;
     int gc = G;
     if (G * mw > slot_words) {
@@ -1634,10 +1719,11 @@ static int plan_geometry(b200l_ctx *c) {
     g.TR = TR; g.S = S; g.slot_bytes = slot_bytes; g.cs = cs; g.cs_shift = cs_shift;
     g.ring_bytes = S * slot_bytes;
     g.nrg = nrg; g.ncg = ncg; g.rows_pad = rows_pad;
-    g.mw = mw; g.gc = gc; g.dchunk = dchunk; g.nown = nown;
+    g.mw = mw; g.gc = gc; g.dchunk = dchunk; g.nown = nown; g.direct_pub = direct;
     g.inflight = c->max_inflight > 0 ? std::min(c->max_inflight, S) : S;
     g.l2_ahead = (c->dbg & 8) ? 0 : 1;
     g.l2_pass = (c->dbg & 16) ? 1 : 0;
+    g.gate_mode = ((c->dbg >> 5) & 3) == 0 ? 2 : (((c->dbg >> 5) & 3) == 3 ? 0 : ((c->dbg >> 5) & 3) == 2 ? 3 : 1);
 
     // inboxes of the partial block gradients: [G readers][G writers][cs][WPC] LL words
     const size_t need = (size_t)G * G * mw * 16;

@@ -169,6 +169,5 @@ class GPU_Calculation:
         keys = ('grid', 'threads', 'smem_bytes', 'tile_rows', 'ring_slots', 'tiles_per_slab')
         return dict(zip(keys, [int(v.value) for v in vals]))
 
-    def set_tuning(self, slot_bytes=0, keep_tiles=-1, inflight=0):
-        _lib.check(self._lib.b200l_set_tuning(self.ctx, int(slot_bytes), int(keep_tiles),
-                                              int(inflight)))
+    def set_tuning(self, slot_bytes=0, inflight=0):
+        _lib.check(self._lib.b200l_set_tuning(self.ctx, int(slot_bytes), int(inflight)))

@@ -28,9 +28,8 @@ def main():
     ap.add_argument("--dtype", default="float")
     ap.add_argument("--sweeps", type=int, default=3)
     ap.add_argument("--slot-bytes", type=int, default=0)
-    ap.add_argument("--keep-tiles", type=int, default=-1)
     ap.add_argument("--inflight", type=int, default=0)
-    ap.add_argument("--sweep", default="", help="semicolon list of slot,keep,inflight[,dbg] tuples")
+    ap.add_argument("--sweep", default="", help="semicolon list of slot,inflight[,dbg] tuples")
     ap.add_argument("--out", default="")
     ap.add_argument("--raw", default="", help="prefix for raw trace dumps (.npy)")
     args = ap.parse_args()
@@ -46,14 +45,14 @@ def main():
     lib, ctx = cal._lib, cal.ctx
     bb = np.ascontiguousarray(b.reshape(-1))
     NT = _lib.NTRACE
-    combos = [(args.slot_bytes, args.keep_tiles, args.inflight, 0)]
+    combos = [(args.slot_bytes, args.inflight, 0)]
     if args.sweep:
         combos = [tuple(int(v) for v in c.split(",")) for c in args.sweep.split(";") if c]
     results = []
     for combo in combos:
-        slot, keep, infl = combo[:3]
-        dbg = combo[3] if len(combo) > 3 else 0
-        cal.set_tuning(slot, keep, infl)
+        slot, infl = combo[:2]
+        dbg = combo[2] if len(combo) > 2 else 0
+        cal.set_tuning(slot, infl)
         _lib.check(lib.b200l_debug_flags(ctx, dbg))
         _lib.check(lib.b200l_set_problem(ctx, _lib.dptr(bb)))
         geo = cal.run_config()
@@ -80,7 +79,7 @@ def main():
         s = t[:, BLOCK:, :]                        # skip the first sweep of the launch
         dur = np.diff(s, axis=2)
         step_len = s[:, 1:, 0] - s[:, :-1, 0]
-        out = {"tuning": {"slot_bytes": slot, "keep": keep, "inflight": infl, "dbg": dbg}, "geo": geo,
+        out = {"tuning": {"slot_bytes": slot, "inflight": infl, "dbg": dbg}, "geo": geo,
                "ms_per_sweep_traced": kms.value / args.sweeps, "ms_per_sweep": float(np.median(ts)),
                "sweeps_per_s": 1e3 / float(np.median(ts)),
                "us_per_block_step": float(step_len.mean()),
@@ -91,8 +90,8 @@ def main():
                "skew_us_step_start": float((s[:, :, 0].max(axis=0) - s[:, :, 0].min(axis=0)).mean())}
         results.append(out)
         if args.raw:
-            np.save("%s_%d_%d_%d_%d.npy" % (args.raw, slot, keep, infl, dbg), tr)
-            np.save("%s_tiles_%d_%d_%d_%d.npy" % (args.raw, slot, keep, infl, dbg), tt[::16])
+            np.save("%s_%d_%d_%d.npy" % (args.raw, slot, infl, dbg), tr)
+            np.save("%s_tiles_%d_%d_%d.npy" % (args.raw, slot, infl, dbg), tt[::16])
         print(json.dumps({k: out[k] for k in ("tuning", "ms_per_sweep", "sweeps_per_s", "us_per_block_step",
                                                "phases_us_mean_over_ctas", "skew_us_pass1_end")}))
         sys.stdout.flush()
