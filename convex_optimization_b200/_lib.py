@@ -20,6 +20,7 @@ HEADER = os.path.join(INCLUDE, "b200lasso.h")
 F32, F64 = 0, 1
 NTRACE = 12
 NTTRACE = 96
+IPC_HANDLE_BYTES = 64
 ROWMAJOR, TRANSPOSED = 0, 1
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
@@ -81,6 +82,9 @@ PROTOTYPES = {
                          ctypes.POINTER(ctypes.c_uint64), _pi32, _pd]),
     "b200l_set_wait_limit": (_c_int, [_p, _c_dbl]),
     "b200l_debug_flags": (_c_int, [_p, _c_i32]),
+    "b200l_comm_export": (_c_int, [_p, _c_i32, _c_i32, _p, _c_i32]),
+    "b200l_comm_connect": (_c_int, [_p, _p, _c_i32]),
+    "b200l_comm_destroy": (_c_int, [_p]),
     "b200l_objective": (_c_int, [_p, _c_dbl, _pd]),
 }
 

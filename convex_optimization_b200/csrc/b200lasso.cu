@@ -28,6 +28,10 @@
 
 #include "b200lasso.h"
 
+#ifndef B200L_MAX_WORLD
+#define B200L_MAX_WORLD 8
+#endif
+
 // ------------------------------------------------------------------------------------
 // error plumbing
 // ------------------------------------------------------------------------------------
@@ -297,7 +301,11 @@ struct RunParams {
     int32_t dbg;          // diagnostics only: 1 skip exchange waits, 2 skip pass-1 math, 4 skip pass-2 math
     unsigned long long wait_limit_ns;
     // geometry
-    int32_t TR, S, slot_bytes, cs, cs_shift, nrg, ncg, rows_pad, inflight, l2_ahead, l2_pass;
+    int32_t TR, S, slot_bytes, cs, cs_shift, nrg, ncg, rows_pad, rows_max_, inflight, l2_ahead, l2_pass;
+    // multi-GPU: rank `rank` of `world` holds column slice `rank` of every block; peer[r] is the
+    // q-inbox of rank r: [2 parities][G CTAs][world sources][qw] words (peer[rank] is local)
+    int32_t world, rank, qw;
+    ulonglong2 *peer[B200L_MAX_WORLD];
     int32_t direct_pub;       // partial gradients are published from registers (one row group)
     int32_t gate_mode;        // 0: re-stream freely, 1/2/3: after inbox fetch issued / gather done / D fetch issued
     int32_t mw, gc, dchunk, nown;   // message words, sources per gather group, D words per fetch, owner CTAs
@@ -1059,6 +1067,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
             }
             cbar();
             if (trace) trace[step * NTRACE + 8] = globaltimer_ns() - t_start;
+            if (p.world > 1) {
+                // ---------------- multi-GPU: sum the partial A_m D over the ranks ----------
+                // (the reduce of lasso.py:126 over the reference's P column slices).  CTA c of
+                // every rank owns the same rows: it stores its rows_c partial sums, plus its
+                // l1 / err terms, as tagged words straight into the inbox of CTA c on every
+                // peer (NVLink peer stores), then adds up the world contributions in rank order,
+                // so every rank holds bitwise the same q and the replicated r stays identical.
+                // Double-buffered by step parity: a rank can be at most one exchange ahead.
+                const int nq = rows_c + 2;
+                const size_t cell = (((size_t)(tag & 1u) * G + c) * p.world) * p.qw;
+#pragma unroll 1
+                for (int i = tid; i < nq; i += NTC) {
+                    const double own = i < rows_c ? qpart[i] : ctl->sp[2 + (i - rows_c)];
+#pragma unroll 1
+                    for (int pr = 0; pr < p.world; ++pr)
+                        if (pr != p.rank) ll_st_dbl(p.peer[pr] + cell + (size_t)p.rank * p.qw + i, own, tag);
+                }
+#pragma unroll 1
+                for (int i = tid; i < nq; i += NTC) {
+                    const double own = i < rows_c ? qpart[i] : ctl->sp[2 + (i - rows_c)];
+                    double acc = 0.0;
+#pragma unroll 1
+                    for (int sr = 0; sr < p.world; ++sr) {
+                        double v = own;
+                        if (sr != p.rank) {
+                            const ulonglong2 *wp = p.peer[p.rank] + cell + (size_t)sr * p.qw + i;
+                            ulonglong2 w = ll_ld(wp);
+                            waiter.begin(((long long)step << 32) | (1LL << 30) | (long long)(sr * 65536 + i));
+                            while (!ll_ok(w, tag) && !(p.dbg & 1)) {
+                                if (!waiter.again()) break;
+                                w = ll_ld(wp);
+                            }
+                            v = ll_dbl(w);
+                        }
+                        acc = (i == rows_c + 1) ? fmax(acc, v) : acc + v;
+                    }
+                    if (i < rows_c) qpart[i] = acc;
+                    else ctl->sp[2 + (i - rows_c)] = acc;
+                }
+            }
             {
                 double trq = 0.0, tqq = 0.0;
 #pragma unroll 1
@@ -1255,6 +1303,10 @@ struct b200l_ctx {
     cudaEvent_t ev0, ev1;
     // tuning
     int32_t slot_target, max_inflight, dbg;
+    // multi-GPU
+    int world, rank;
+    ulonglong2 *peer[B200L_MAX_WORLD];   // peer[rank] = own inbox (cudaMalloc), others IPC-mapped
+    size_t inbox_bytes;
     // cached geometry
     RunParams geo;
     int grid, smem_bytes, cpt, nt_max;
@@ -1263,6 +1315,8 @@ struct b200l_ctx {
 };
 
 static int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+static int comm_release(b200l_ctx *c);
+static int plan_geometry(b200l_ctx *c);
 
 extern "C" const char *b200l_last_error(void) { return g_err; }
 extern "C" int b200l_abi_version(void) { return B200L_ABI_VERSION; }
@@ -1335,6 +1389,8 @@ extern "C" int b200l_ctx_create(b200l_ctx **out, int dtype, int layout, int64_t 
     c->slot_target = 65536;
     c->max_inflight = 0;
     c->wait_limit_ns = 5000000000ULL;
+    c->world = 1;
+    c->rank = 0;
 
     const int64_t nx = (int64_t)nblocks * c->xld;
     const int64_t vmax = std::max<int64_t>(std::max<int64_t>(N, K), nx) + 64;
@@ -1375,6 +1431,7 @@ extern "C" int b200l_ctx_destroy(b200l_ctx *c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    comm_release(c);
     void *ptrs[] = {c->x, c->d, c->drec, c->dsum, c->r, c->b, c->vin, c->vout, c->part, c->gLL,
                     c->dLL, c->abort_flag, c->gamma_state, c->objbuf, c->state, c->err_hist,
                     c->time_hist, c->trace, c->ttrace, c->order};
@@ -1718,7 +1775,7 @@ static int plan_geometry(b200l_ctx *c) {
     const int dchunk = std::min(ld + (G - nown), slot_words);
     g.TR = TR; g.S = S; g.slot_bytes = slot_bytes; g.cs = cs; g.cs_shift = cs_shift;
     g.ring_bytes = S * slot_bytes;
-    g.nrg = nrg; g.ncg = ncg; g.rows_pad = rows_pad;
+    g.nrg = nrg; g.ncg = ncg; g.rows_pad = rows_pad; g.rows_max_ = rows_max;
     g.mw = mw; g.gc = gc; g.dchunk = dchunk; g.nown = nown; g.direct_pub = direct;
     g.inflight = c->max_inflight > 0 ? std::min(c->max_inflight, S) : S;
     g.l2_ahead = (c->dbg & 8) ? 0 : 1;
@@ -1821,6 +1878,10 @@ static int launch_fused(b200l_ctx *c, const int32_t *order_host, int64_t nsteps,
     p.ttrace = ttrace_dev;
     p.tag_base = c->tag_base;
     p.wait_limit_ns = c->wait_limit_ns;
+    p.world = c->world;
+    p.rank = c->rank;
+    p.qw = c->world > 1 ? (int32_t)round_up(c->geo.rows_max_ + 2, 2) : 0;
+    for (int r = 0; r < B200L_MAX_WORLD; ++r) p.peer[r] = c->peer[r];
     p.dbg = c->dbg;
 
     fused_fn fn = ctx_kernel(c);
@@ -1939,4 +2000,68 @@ extern "C" int b200l_debug_flags(b200l_ctx *c, int32_t flags) {
     c->dbg = flags;
     c->geo_valid = 0;
     return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// multi-GPU: one process per GPU, column slice `rank` of every block per rank
+// ------------------------------------------------------------------------------------
+static int comm_release(b200l_ctx *c) {
+    for (int r = 0; r < B200L_MAX_WORLD; ++r) {
+        if (!c->peer[r]) continue;
+        if (r == c->rank) cudaFree(c->peer[r]);
+        else cudaIpcCloseMemHandle(c->peer[r]);
+        c->peer[r] = nullptr;
+    }
+    c->world = 1;
+    c->rank = 0;
+    c->inbox_bytes = 0;
+    return 0;
+}
+
+extern "C" int b200l_comm_export(b200l_ctx *c, int32_t rank, int32_t world, void *handle_out,
+                                 int32_t handle_bytes) {
+    if (!c || !handle_out) return fail("NULL argument");
+    if (world < 2 || world > B200L_MAX_WORLD) return fail("world must be 2..%d", B200L_MAX_WORLD);
+    if (rank < 0 || rank >= world) return fail("rank %d out of range", rank);
+    if (handle_bytes < (int32_t)sizeof(cudaIpcMemHandle_t))
+        return fail("handle buffer must hold %d bytes", (int)sizeof(cudaIpcMemHandle_t));
+    CK(cudaSetDevice(c->device));
+    if (plan_geometry(c)) return 1;
+    comm_release(c);
+    const size_t qw = (size_t)round_up(c->geo.rows_max_ + 2, 2);
+    const size_t bytes = 2 * (size_t)c->grid * world * qw * 16;
+    ulonglong2 *buf = nullptr;
+    CK(cudaMalloc((void **)&buf, bytes));
+    CK(cudaMemset(buf, 0, bytes));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, buf));
+    memcpy(handle_out, &h, sizeof(h));
+    c->world = world;
+    c->rank = rank;
+    c->peer[rank] = buf;
+    c->inbox_bytes = bytes;
+    return 0;
+}
+
+extern "C" int b200l_comm_connect(b200l_ctx *c, const void *all_handles, int32_t handle_stride) {
+    if (!c || !all_handles) return fail("NULL argument");
+    if (c->world < 2 || !c->peer[c->rank]) return fail("b200l_comm_export has not been called");
+    if (handle_stride < (int32_t)sizeof(cudaIpcMemHandle_t)) return fail("handle stride too small");
+    CK(cudaSetDevice(c->device));
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)all_handles + (size_t)r * handle_stride, sizeof(h));
+        void *ptr = nullptr;
+        CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer[r] = (ulonglong2 *)ptr;
+    }
+    return 0;
+}
+
+extern "C" int b200l_comm_destroy(b200l_ctx *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    return comm_release(c);
 }

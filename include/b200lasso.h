@@ -146,6 +146,24 @@ int b200l_set_wait_limit(b200l_ctx *ctx, double seconds);
  * pass-2 arithmetic of the fused kernel, to time the remaining parts.  Results are invalid. */
 int b200l_debug_flags(b200l_ctx *ctx, int32_t flags);
 
+/* -- multi-GPU: one process per GPU ------------------------------------------------
+ * Rank `rank` of `world` creates its context with the LOCAL column count (K/world): column
+ * slice `rank` of every block, exactly the reference's P-way split of a block
+ * (cpu_calculation.py:23-27 with P = world).  Each rank owns its x columns; the residual r
+ * is replicated.  Inside the fused kernel the partial products A_{m,rank} D_rank are
+ * summed over the ranks through peer memory (the reduce of lasso.py:126), in rank order, so
+ * all ranks hold bitwise the same q, gamma and r.  mu and b must be identical on all ranks
+ * and all ranks must call b200l_run with the same arguments.
+ * comm_export : allocate this rank's inbox and return its CUDA IPC handle (64 bytes);
+ * comm_connect: given the handles of all ranks (rank-major, handle_stride bytes apart,
+ *               e.g. from an all-gather), map the peers' inboxes.
+ * world = 1 (default) needs neither. */
+#define B200L_MAX_WORLD 8
+#define B200L_IPC_HANDLE_BYTES 64
+int b200l_comm_export(b200l_ctx *ctx, int32_t rank, int32_t world, void *handle_out, int32_t handle_bytes);
+int b200l_comm_connect(b200l_ctx *ctx, const void *all_handles, int32_t handle_stride);
+int b200l_comm_destroy(b200l_ctx *ctx);
+
 /* 0.5*|r|^2 + mu*|x|_1 from the device state (lasso.py:46-47 with the running residual) */
 int b200l_objective(b200l_ctx *ctx, double mu, double *value);
 

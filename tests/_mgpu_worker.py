@@ -1,0 +1,74 @@
+"""torchrun worker of tests/test_multi_gpu.py: column-sharded fused solve on `world` GPUs vs the
+oracle (which follows the reference's P-way split, lasso.py:107-126)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from oracle import lasso_oracle as orc
+    from convex_optimization_b200 import distributed as dd
+    from convex_optimization_b200 import lasso
+    from convex_optimization_b200.gpu_calculation import GPU_Calculation
+
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = True
+    cases = [(300, 2400, 4, 0.05, "double", 7), (257, 1024 * world, 8, 0.03, "double", 11),
+             (1000, 8000, 2, 0.02, "float", 5), (64, 64 * world, 1, 0.2, "double", 3)]
+    for (N, K, BLOCK, den, TYPE, seed) in cases:
+        A, _, b, mu = orc.make_problem(N, K, den, seed=seed)
+        if TYPE == "float":
+            A = A.astype(np.float32).astype(np.float64)
+        ITER_MAX = 80 * BLOCK
+        o = orc.lasso_oracle(A, b, mu, BLOCK, ITER_MAX, 1e-4, P=world, faithful=False)
+
+        class Cal(GPU_Calculation):
+            pass
+        Cal.TYPE = TYPE
+        Cal.DEVICE = local
+        A_loc = dd.shard_columns(A, BLOCK, rank, world)
+        cal = Cal(A_loc, BLOCK)
+        dd.connect(cal)
+        solver = lasso.ClassLasso(cal, cal.diag_ATA, A_loc, b, mu, BLOCK, ITER_MAX)
+        err_iter = np.zeros(ITER_MAX)
+        solver.run(1e-4, err_iter=err_iter, SILENCE=True)
+        x = dd.gather_x(solver.x, BLOCK)
+        tol = 1e-10 if TYPE == "double" else 1e-5
+        rel = np.abs(x - o["x"]).max() / np.abs(o["x"]).max()
+        same_iters = solver.iters == o["iters"] if TYPE == "double" else abs(solver.iters - o["iters"]) <= BLOCK
+        supp = np.array_equal(x != 0, o["x"] != 0) if TYPE == "double" else True
+        n = min(solver.iters, o["iters"])
+        errs = np.abs(err_iter[:n] - o["err"][:n]).max()
+        # every rank must hold bitwise the same trace (replicated r and gamma)
+        t = torch.from_numpy(err_iter.copy()).cuda()
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        same_trace = all(torch.equal(parts[0], p) for p in parts)
+        good = bool(rel < tol and same_iters and supp and errs < max(tol, 1e-10) and same_trace)
+        ok = ok and good
+        if rank == 0:
+            print("case N=%d K=%d BLOCK=%d %s world=%d: iters %d/%d rel %.2e err-trace %.2e support %s same-trace %s -> %s"
+                  % (N, K, BLOCK, TYPE, world, solver.iters, o["iters"], rel, errs, supp, same_trace,
+                     "ok" if good else "FAIL"))
+        dd.disconnect(cal)
+        del solver, cal
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(flag)
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MGPU_RESULT", "OK" if int(flag.item()) == 0 else "FAIL")
+    return 0 if int(flag.item()) == 0 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
