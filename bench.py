@@ -114,12 +114,18 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ data
-def make_device_instance(torch, device, N, K, BLOCK, den, seed, torch_dtype, ld, layout="row"):
+def make_device_instance(torch, device, N, K, BLOCK, den, seed, torch_dtype, ld, layout="row",
+                         dist=None, rank=0):
     """reference recipe (parameters.py:20-33) on the device: Gaussian A, unit-l2 rows,
-    sparse x_true, b = A x_true + e, mu = 0.1 |A^T b|_inf.  Returns (store, b, mu)."""
+    sparse x_true, b = A x_true + e, mu = 0.1 |A^T b|_inf.  Returns (store, b, mu).
+    With ``dist`` (multi-GPU) every rank generates its own column shard (K local columns,
+    seed + rank); row norms, b and mu are combined over the ranks, the noise e is the same
+    on every rank."""
     w = K // BLOCK
     gen = torch.Generator(device=device)
-    gen.manual_seed(seed)
+    gen.manual_seed(seed + 1000 * rank)
+    gen_common = torch.Generator(device=device)
+    gen_common.manual_seed(seed + 77)
     rows = N if layout == "row" else w
     store = torch.zeros((BLOCK, rows, ld), dtype=torch_dtype, device=device)
     sq = torch.zeros(N, dtype=torch.float64, device=device)
@@ -130,6 +136,8 @@ def make_device_instance(torch, device, N, K, BLOCK, den, seed, torch_dtype, ld,
             store[m, :, :w] = blk
         else:
             store[m, :, :N] = blk.t()
+    if dist is not None:
+        dist.all_reduce(sq)
     inv = (1.0 / sq.sqrt()).to(torch_dtype)
     x_true = torch.randn(K, generator=gen, dtype=torch.float64, device=device)
     x_true *= (torch.rand(K, generator=gen, dtype=torch.float64, device=device) < den)
@@ -141,7 +149,9 @@ def make_device_instance(torch, device, N, K, BLOCK, den, seed, torch_dtype, ld,
         else:
             store[m, :, :N] *= inv[None, :]
             b += store[m, :, :N].double().t() @ x_true[m * w:(m + 1) * w]
-    b += 1e-2 * torch.randn(N, generator=gen, dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(b)
+    b += 1e-2 * torch.randn(N, generator=gen_common, dtype=torch.float64, device=device)
     gmax = 0.0
     for m in range(BLOCK):
         if layout == "row":
@@ -149,6 +159,10 @@ def make_device_instance(torch, device, N, K, BLOCK, den, seed, torch_dtype, ld,
         else:
             g = store[m, :, :N].double() @ b
         gmax = max(gmax, float(g.abs().max()))
+    if dist is not None:
+        t = torch.tensor([gmax], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gmax = float(t.item())
     return store, b.cpu().numpy().reshape(-1, 1), 0.1 * gmax
 
 
@@ -246,9 +260,14 @@ def main_gpu(args):
         DEVICE = local_rank
     ld = Cal.padded_ld(N, K, BLOCK)
     tdt = torch.float32 if cfg["dtype"] == "float" else torch.float64
-    store, b, mu = make_device_instance(torch, device, N, K, BLOCK, cfg["den"], cfg["seed"] + rank,
-                                        tdt, ld, layout)
+    # N GPUs: the instance grows with N (weak scaling): K = 100000*N columns, 100 blocks of width
+    # 1000*N, column slice `rank` of every block per GPU, i.e. one C2-sized shard per GPU
+    store, b, mu = make_device_instance(torch, device, N, K, BLOCK, cfg["den"], cfg["seed"], tdt, ld, layout,
+                                        dist if world > 1 else None, rank)
     cal = Cal.from_device_blocks(store, N, K, BLOCK)
+    if world > 1:
+        from convex_optimization_b200 import distributed as dd
+        dd.connect(cal)
     if args.slot_bytes or args.inflight:
         cal.set_tuning(args.slot_bytes, args.inflight)
     lib, ctx = cal._lib, cal.ctx
@@ -340,10 +359,13 @@ def main_gpu(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32" if s == 4 else "f64",
             "data": "synthetic",
             "config": {"workload": "dense %s lasso %dx%d, %d column blocks, %s A layout; 1 step = 1 sweep; "
-                                   "A=%.1f GB >> L2 so no flush between steps%s"
-                                   % ("fp32" if s == 4 else "fp64", N, K, BLOCK, layout,
+                                   "A=%.1f GB per GPU >> L2 so no flush between steps%s"
+                                   % ("fp32" if s == 4 else "fp64", N, K * world, BLOCK, layout,
                                       N * K * s / 1e9,
-                                      "; one independent instance per GPU (replicas)" if world > 1 else ""),
+                                      ("; column-sharded over %d GPUs (slice g of every block on GPU g, partial "
+                                       "A_m D summed in-kernel over NVLink peer memory); value counts C2-sized "
+                                       "shard sweeps: %d per sweep of the %dx%d instance"
+                                       % (world, world, N, K * world)) if world > 1 else ""),
                        "launch": geo, "objective_after_bench": obj.value},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
@@ -366,6 +388,7 @@ def main_gpu(args):
             line["cpu_baseline"] = cpu_baseline_block()
         print(json.dumps(line))
     if world > 1:
+        dd.disconnect(cal)
         dist.destroy_process_group()
     return 0
 

@@ -311,7 +311,7 @@ struct RunParams {
     int32_t mw, gc, dchunk, nown;   // message words, sources per gather group, D words per fetch, owner CTAs
     // shared-memory offsets
     int32_t off_bar, off_ctl, off_rloc, off_qloc, off_rT, off_qT, off_delta, off_redT, off_colsum,
-        off_small, off_qpart, ring_bytes;
+        off_small, off_qpart, off_qx, ring_bytes;
 };
 
 // bounded spinning: returns false when the wait has to be abandoned (a peer timed out or
@@ -1009,6 +1009,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
 
             // ---------------- pass 2: q = A_m D over the slab ---------------------------
             {
+                // multi-GPU: a finished row of the partial product goes to the peers at once, so
+                // the NVLink latency overlaps the rest of the pass (see the exchange below)
+                const size_t cell = (((size_t)(tag & 1u) * G + c) * p.world) * p.qw;
+                auto send_row = [&](int idx, double v) {
+                    if (p.world > 1) {
+#pragma unroll 1
+                        for (int pr = 0; pr < p.world; ++pr)
+                            if (pr != p.rank) ll_st_dbl(p.peer[pr] + cell + (size_t)p.rank * p.qw + idx, v, tag);
+                    }
+                };
+                if (tid == 0) {            // my l1 / err terms of this step travel with the rows
+                    send_row(rows_c, ctl->sp[2]);
+                    send_row(rows_c + 1, ctl->sp[3]);
+                }
                 // one row of the tile against D: partial sum of this lane's column groups
                 auto row_dot = [&](const T *trow) -> T {
                     Acc a0, a1;
@@ -1053,11 +1067,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                             const T qa = row_dot(tile + (size_t)rr * ld);
                             const T qb = row_dot(tile + (size_t)(rr + NW) * ld);
                             const T qs = warp_sum_pair(qa, qb, lane);
-                            if ((lane & 15) == 0) qpart[t * TR + rr + (lane >> 4) * NW] = (double)qs;
+                            if ((lane & 15) == 0) {
+                                const int row = t * TR + rr + (lane >> 4) * NW;
+                                qpart[row] = (double)qs;
+                                send_row(row, (double)qs);
+                            }
                         }
                         if (rr < rows_t) {
                             const T qs = warp_sum(row_dot(tile + (size_t)rr * ld));
-                            if (lane == 0) qpart[t * TR + rr] = (double)qs;
+                            if (lane == 0) {
+                                qpart[t * TR + rr] = (double)qs;
+                                send_row(t * TR + rr, (double)qs);
+                            }
                         }
                     }
                     __syncwarp();
@@ -1070,37 +1091,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
             if (p.world > 1) {
                 // ---------------- multi-GPU: sum the partial A_m D over the ranks ----------
                 // (the reduce of lasso.py:126 over the reference's P column slices).  CTA c of
-                // every rank owns the same rows: it stores its rows_c partial sums, plus its
-                // l1 / err terms, as tagged words straight into the inbox of CTA c on every
-                // peer (NVLink peer stores), then adds up the world contributions in rank order,
+                // every rank owns the same rows; during pass 2 it stored its rows_c partial sums
+                // and its l1 / err terms as tagged words straight into the inbox of CTA c on every
+                // peer (NVLink peer stores).  Here it collects the world-1 contributions (threads
+                // = (word, source) pairs, through shared memory) and adds them up in rank order,
                 // so every rank holds bitwise the same q and the replicated r stays identical.
                 // Double-buffered by step parity: a rank can be at most one exchange ahead.
                 const int nq = rows_c + 2;
                 const size_t cell = (((size_t)(tag & 1u) * G + c) * p.world) * p.qw;
+                double *qx = reinterpret_cast<double *>(smem + p.off_qx);      // [world-1][qw]
 #pragma unroll 1
-                for (int i = tid; i < nq; i += NTC) {
-                    const double own = i < rows_c ? qpart[i] : ctl->sp[2 + (i - rows_c)];
-#pragma unroll 1
-                    for (int pr = 0; pr < p.world; ++pr)
-                        if (pr != p.rank) ll_st_dbl(p.peer[pr] + cell + (size_t)p.rank * p.qw + i, own, tag);
+                for (int e = tid; e < nq * (p.world - 1); e += NTC) {
+                    const int k = e / nq, i = e - k * nq;
+                    const int sr = k < p.rank ? k : k + 1;
+                    const ulonglong2 *wp = p.peer[p.rank] + cell + (size_t)sr * p.qw + i;
+                    ulonglong2 w = ll_ld(wp);
+                    waiter.begin(((long long)step << 32) | (1LL << 30) | (long long)(sr * 65536 + i));
+                    while (!ll_ok(w, tag) && !(p.dbg & 1)) {
+                        if (!waiter.again()) break;
+                        w = ll_ld(wp);
+                    }
+                    qx[k * p.qw + i] = ll_dbl(w);
                 }
+                cbar();
 #pragma unroll 1
                 for (int i = tid; i < nq; i += NTC) {
                     const double own = i < rows_c ? qpart[i] : ctl->sp[2 + (i - rows_c)];
                     double acc = 0.0;
 #pragma unroll 1
                     for (int sr = 0; sr < p.world; ++sr) {
-                        double v = own;
-                        if (sr != p.rank) {
-                            const ulonglong2 *wp = p.peer[p.rank] + cell + (size_t)sr * p.qw + i;
-                            ulonglong2 w = ll_ld(wp);
-                            waiter.begin(((long long)step << 32) | (1LL << 30) | (long long)(sr * 65536 + i));
-                            while (!ll_ok(w, tag) && !(p.dbg & 1)) {
-                                if (!waiter.again()) break;
-                                w = ll_ld(wp);
-                            }
-                            v = ll_dbl(w);
-                        }
+                        const double v = sr == p.rank ? own : qx[(sr < p.rank ? sr : sr - 1) * p.qw + i];
                         acc = (i == rows_c + 1) ? fmax(acc, v) : acc + v;
                     }
                     if (i < rows_c) qpart[i] = acc;
@@ -1731,10 +1751,12 @@ static int plan_geometry(b200l_ctx *c) {
         const int o_colsum = take(2 * (4 + MAX_CS) * 16);         // gathered scalars + columns (+ group sums)
         const int o_small = take((2 * MAX_CS + 2 * NW) * 8);      // l1s, es, lsred
         const int o_qpart = take(rows_pad * 8);
+        const int o_qx = take(c->world > 1 ? (c->world - 1) * (int)round_up(rows_max + 2, 2) * 8 : 16);
         if (out) {
             out->off_bar = o_bar; out->off_ctl = o_ctl; out->off_rloc = o_rloc; out->off_qloc = o_qloc;
             out->off_rT = o_rT; out->off_qT = o_qT; out->off_delta = o_delta; out->off_redT = o_redT;
             out->off_colsum = o_colsum; out->off_small = o_small; out->off_qpart = o_qpart;
+            out->off_qx = o_qx;
         }
     };
     // the ring goes first (offset 0); sized after the fixed part is known
@@ -2015,6 +2037,7 @@ static int comm_release(b200l_ctx *c) {
     c->world = 1;
     c->rank = 0;
     c->inbox_bytes = 0;
+    c->geo_valid = 0;
     return 0;
 }
 
@@ -2026,8 +2049,11 @@ extern "C" int b200l_comm_export(b200l_ctx *c, int32_t rank, int32_t world, void
     if (handle_bytes < (int32_t)sizeof(cudaIpcMemHandle_t))
         return fail("handle buffer must hold %d bytes", (int)sizeof(cudaIpcMemHandle_t));
     CK(cudaSetDevice(c->device));
-    if (plan_geometry(c)) return 1;
     comm_release(c);
+    c->world = world;               // the shared-memory plan depends on it
+    c->rank = rank;
+    c->geo_valid = 0;
+    if (plan_geometry(c)) { c->world = 1; c->rank = 0; c->geo_valid = 0; return 1; }
     const size_t qw = (size_t)round_up(c->geo.rows_max_ + 2, 2);
     const size_t bytes = 2 * (size_t)c->grid * world * qw * 16;
     ulonglong2 *buf = nullptr;
