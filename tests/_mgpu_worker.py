@@ -29,8 +29,11 @@ def main():
         A, _, b, mu = orc.make_problem(N, K, den, seed=seed)
         if TYPE == "float":
             A = A.astype(np.float32).astype(np.float64)
-        ITER_MAX = 80 * BLOCK
-        o = orc.lasso_oracle(A, b, mu, BLOCK, ITER_MAX, 1e-4, P=world, faithful=False)
+        # fp32 is compared after a fixed number of iterations: at ERR_BOUND the fp32 error can land
+        # on either side of the threshold and the two runs would stop one sweep apart
+        ITER_MAX = 80 * BLOCK if TYPE == "double" else 12 * BLOCK
+        bound = 1e-4 if TYPE == "double" else None
+        o = orc.lasso_oracle(A, b, mu, BLOCK, ITER_MAX, bound, P=world, faithful=False)
 
         class Cal(GPU_Calculation):
             pass
@@ -41,12 +44,13 @@ def main():
         dd.connect(cal)
         solver = lasso.ClassLasso(cal, cal.diag_ATA, A_loc, b, mu, BLOCK, ITER_MAX)
         err_iter = np.zeros(ITER_MAX)
-        solver.run(1e-4, err_iter=err_iter, SILENCE=True)
+        solver.run(bound, err_iter=err_iter, SILENCE=True)
         x = dd.gather_x(solver.x, BLOCK)
         tol = 1e-10 if TYPE == "double" else 1e-5
         rel = np.abs(x - o["x"]).max() / np.abs(o["x"]).max()
-        same_iters = solver.iters == o["iters"] if TYPE == "double" else abs(solver.iters - o["iters"]) <= BLOCK
-        supp = np.array_equal(x != 0, o["x"] != 0) if TYPE == "double" else True
+        same_iters = solver.iters == o["iters"]
+        big = np.abs(o["x"]) > 1e-5 * np.abs(o["x"]).max()
+        supp = np.array_equal(x != 0, o["x"] != 0) if TYPE == "double" else np.array_equal((x != 0)[big], (o["x"] != 0)[big])
         n = min(solver.iters, o["iters"])
         errs = np.abs(err_iter[:n] - o["err"][:n]).max()
         # every rank must hold bitwise the same trace (replicated r and gamma)
