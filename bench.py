@@ -369,7 +369,9 @@ def main_gpu(args):
                        "launch": geo, "objective_after_bench": obj.value},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "lasso_fused_rowmajor", "kernel_ms_per_launch": kernel_ms,
+                         "kernel": "lasso_fused<%s,1,%s>" % ("float" if s == 4 else "double",
+                                                             "TRANS" if layout == "transposed" else "ROWMAJOR"),
+                         "kernel_ms_per_launch": kernel_ms,
                          "kernel_ms_per_launch_alone": kernel_ms_alone,
                          "algorithmic_bytes_per_launch": W, "peak_source": peak_src,
                          "frac_of_nominal_8TBs": achieved / 8000.0,

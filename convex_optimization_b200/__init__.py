@@ -10,13 +10,14 @@ ctypes in ``_lib``; there is no CPU fallback for the device classes.
 from . import _lib                                   # noqa: F401
 from . import cpu_calculation, parameters, settings  # noqa: F401
 
-__all__ = ["_lib", "cpu_calculation", "parameters", "settings", "gpu_calculation", "lasso"]
+__all__ = ["_lib", "cpu_calculation", "parameters", "settings", "gpu_calculation", "lasso", "path",
+           "distributed"]
 __version__ = "0.1.0"
 
 
 def __getattr__(name):
     # gpu_calculation / lasso import torch lazily through GPU_Calculation only
-    if name in ("gpu_calculation", "lasso"):
+    if name in ("gpu_calculation", "lasso", "path", "distributed"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

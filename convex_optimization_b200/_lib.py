@@ -73,6 +73,7 @@ PROTOTYPES = {
     "b200l_set_problem": (_c_int, [_p, _pd]),
     "b200l_reset": (_c_int, [_p]),
     "b200l_set_x": (_c_int, [_p, _pd]),
+    "b200l_restart_counters": (_c_int, [_p]),
     "b200l_get_x": (_c_int, [_p, _pd]),
     "b200l_get_r": (_c_int, [_p, _pd]),
     "b200l_run": (_c_int, [_p, _pi32, _c_i64, _c_dbl, _c_dbl, _pd, _pd, _pi64, _pi32, _pd]),

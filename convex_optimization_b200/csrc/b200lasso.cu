@@ -17,6 +17,7 @@
 // CTA cross CTAs, through L2, with two grid barriers per block step.  The step size of
 // block t is resolved lazily at the first barrier of block t+1
 // (g_{t+1} = A^T r + gamma A^T q), which removes the third barrier.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdint.h>
@@ -126,6 +127,19 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
             "r"(smem_u32(dst_smem)),
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+// TMA 2-D tiled copy global -> shared through a tensor map (SASS: UTMALDG), and its L2 prefetch
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *tmap, int x, int y,
+                                            uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *tmap, int x, int y) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(x), "r"(y)
+                 : "memory");
 }
 // TMA prefetch of a contiguous range into L2 (no shared memory involved; SASS: UBLKPF)
 __device__ __forceinline__ void tma_prefetch_l2(const void *src_gmem, uint32_t bytes) {
@@ -308,6 +322,9 @@ struct RunParams {
     ulonglong2 *peer[B200L_MAX_WORLD];
     int32_t direct_pub;       // partial gradients are published from registers (one row group)
     int32_t gate_mode;        // 0: re-stream freely, 1/2/3: after inbox fetch issued / gather done / D fetch issued
+    // transposed layout: a tile is TJ block columns x BX residual entries of this CTA
+    // (BX/V odd: conflict-free 16-byte reads with lanes on consecutive columns)
+    int32_t BX, BXV, TJ, nparts, nt_t, off_red2;
     int32_t mw, gc, dchunk, nown;   // message words, sources per gather group, D words per fetch, owner CTAs
     // shared-memory offsets
     int32_t off_bar, off_ctl, off_rloc, off_qloc, off_rT, off_qT, off_delta, off_redT, off_colsum,
@@ -439,8 +456,12 @@ __device__ __forceinline__ T warp_sum_pair(const T a, const T b, const int lane)
 // CPT : column groups (16-byte vectors) per thread in pass 1 (ld/V <= CPT*NTC).  CPT == 1 also
 //       means at most 8 column groups per lane in pass 2, whose slice of the step D then lives
 //       in registers; wider blocks read D from shared memory.
-template <typename T, int CPT>
-__global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunParams p) {
+// TRANS: blocks are stored pre-transposed, (w, ldT >= N) row-major per block; a CTA's share of a
+//       block is then a 2-D box (all columns x its residual entries), fetched tile by tile
+//       through a tensor map.  Pass 1 is a row-dot per column (thread = column), pass 2 an
+//       axpy over columns (thread = (16-byte group of residual entries, column part)).
+template <typename T, int CPT, bool TRANS>
+__global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, const __grid_constant__ CUtensorMap tmap) {
     using VecT = typename VT<T>::type;
     using LL = LLW<T>;
     using OP = Ops<T>;
@@ -468,12 +489,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int c = blockIdx.x, G = gridDim.x;
-    const int64_t base = p.N / G;
-    const int rem = (int)(p.N % G);
-    const int rows_c = (int)base + (c < rem ? 1 : 0);
-    const int64_t row0 = (int64_t)c * base + (c < rem ? c : rem);
+    // rows of this CTA: an even split of N (TRANS: of the 16-byte groups of N, because the inner
+    // coordinate of a tensor-map box has to be 16-byte aligned)
+    const int64_t nunits = TRANS ? (p.N + V - 1) / V : p.N;
+    const int64_t base = nunits / G;
+    const int rem = (int)(nunits % G);
+    const int64_t unit0 = (int64_t)c * base + (c < rem ? c : rem);
+    const int64_t row0 = TRANS ? unit0 * V : unit0;
+    const int rows_c = TRANS ? (int)max((int64_t)0, min((base + (c < rem ? 1 : 0)) * V, p.N - row0))
+                             : (int)base + (c < rem ? 1 : 0);
     const int TR = p.TR, S = p.S, ld = p.ld, ncg = p.ncg;
-    const int nt = (rows_c + TR - 1) / TR;
+    const int nt = TRANS ? (rows_c > 0 ? p.nt_t : 0) : (rows_c + TR - 1) / TR;
     const T *Aall = reinterpret_cast<const T *>(p.A);
 
     // the ring starts zero-filled: rows of a ragged last tile that no copy ever wrote are
@@ -520,6 +546,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                     const int mn = p.order ? p.order[step + 1] : mc;
                     An = reinterpret_cast<const unsigned char *>(Aall + (int64_t)mn * p.blk_stride + row0 * (int64_t)ld);
                 }
+                const int ym = m * p.w, yn = (p.order ? (step + 1 < p.nsteps ? p.order[step + 1] : 0) : mc) * p.w;
                 for (int pass = 0; pass < 2 && live; ++pass) {
                     // the re-stream for pass 2 is held back until the consumers have their
                     // exchange fetch in flight: it would otherwise sit in front of it in the
@@ -547,13 +574,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                             if (*stopf) { live = false; break; }
                         }
                         if (!live) break;
-                        const uint32_t bytes = t == nt - 1 ? last_bytes : tile_bytes;
-                        mbar_expect_tx(full + cur.slot, bytes);
-                        tma_bulk_g2s(ring + (size_t)cur.slot * p.slot_bytes, Ab + (size_t)t * tile_bytes, bytes,
-                                     full + cur.slot);
-                        // HBM runs one block ahead of the passes: while this step re-streams its
-                        // slab for pass 2 (L2 hits), pull the slab of the next step into L2
-                        if (pass == 1 - p.l2_pass && An) tma_prefetch_l2(An + (size_t)t * tile_bytes, bytes);
+                        if (TRANS) {
+                            mbar_expect_tx(full + cur.slot, (uint32_t)(p.TJ * p.BX) * (uint32_t)sizeof(T));
+                            tma_load_2d(ring + (size_t)cur.slot * p.slot_bytes, &tmap, (int)row0, ym + t * p.TJ,
+                                        full + cur.slot);
+                            if (pass == 1 - p.l2_pass && An) tma_prefetch_2d(&tmap, (int)row0, yn + t * p.TJ);
+                        } else {
+                            const uint32_t bytes = t == nt - 1 ? last_bytes : tile_bytes;
+                            mbar_expect_tx(full + cur.slot, bytes);
+                            tma_bulk_g2s(ring + (size_t)cur.slot * p.slot_bytes, Ab + (size_t)t * tile_bytes, bytes,
+                                         full + cur.slot);
+                            // HBM runs one block ahead of the passes: while this step re-streams its
+                            // slab for pass 2 (L2 hits), pull the slab of the next step into L2
+                            if (pass == 1 - p.l2_pass && An) tma_prefetch_l2(An + (size_t)t * tile_bytes, bytes);
+                        }
                         if (p.ttrace && t < 16)
                             p.ttrace[((size_t)c * p.nsteps + step) * NTTRACE + 64 + pass * 16 + t] = globaltimer_ns();
                         cur.advance(S);
@@ -574,6 +608,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
             qT[i] = (T)0;
         }
         for (int i = rows_c + tid; i < p.rows_pad; i += NTC) { rT[i] = (T)0; qT[i] = (T)0; }
+        if (TRANS)
+            for (int i = tid; i < p.nt_t * p.TJ; i += NTC) delta_s[i] = (T)0;   // columns past ld stay 0
         cbar();
 
         unsigned long long kc = 0;
@@ -656,7 +692,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                     const T *tile = reinterpret_cast<const T *>(ring + (size_t)cur.slot * p.slot_bytes);
                     const int rows_t = min(TR, rows_c - t * TR);
                     const T *rTt = rT + t * TR, *qTt = qT + t * TR;
-                    if (p1_active && !(p.dbg & 2)) {
+                    if (TRANS) {
+                        // thread = block column t*TJ + tid: dot products of its BX entries with r and q,
+                        // complete for this CTA's rows, published at once (one tagged word per column)
+                        const int j = t * p.TJ + tid;
+                        Acc a0, a1;
+                        OP::zero(a0);
+                        OP::zero(a1);
+                        if (j < p.w && !(p.dbg & 2)) {
+                            const T *col = tile + (size_t)tid * p.BX;
+#pragma unroll 4
+                            for (int iv = 0; iv < p.BXV; ++iv) {
+                                const VecT v = *reinterpret_cast<const VecT *>(col + iv * V);
+                                OP::mac(a0, v, *reinterpret_cast<const VecT *>(rT + iv * V));
+                                OP::mac(a1, v, *reinterpret_cast<const VecT *>(qT + iv * V));
+                            }
+                        }
+                        if (j < G * cs) {
+                            const int rd = j >> p.cs_shift;
+                            const int jj = j & (cs - 1);
+                            LL::put(p.gLL + ((size_t)rd * G + c) * p.mw + 4 + jj * WPC, OP::hsum(a0), OP::hsum(a1), tag);
+                        }
+                    } else if (p1_active && !(p.dbg & 2)) {
                         if (TR >= 4) {
                             // whole quads: rows past rows_t hold finite stale data and meet r = q = 0
                             const int nquad = (rows_t + 3) >> 2;
@@ -711,7 +768,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                 // when every thread holds complete column sums (one row group) the partial
                 // gradient goes out straight from registers: the V columns of a column group
                 // are 4 adjacent words of one reader's message, two 256-bit stores
-                if (p.direct_pub) {
+                if (TRANS) {
+                    // published tile by tile above
+                } else if (p.direct_pub) {
                     if (p1_active) {
 #pragma unroll
                         for (int k = 0; k < CPT; ++k) {
@@ -763,7 +822,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                 } else {
                     // columns past ld (readers' padding columns) still have to carry the tag
 #pragma unroll 1
-                    for (int j = ncg * V + tid; j < G * cs; j += NTC) {
+                    for (int j = (TRANS ? nt * p.TJ : ncg * V) + tid; j < G * cs; j += NTC) {
                         const int rd = j >> p.cs_shift;
                         const int jj = j & (cs - 1);
                         LL::put(out + (size_t)rd * G * MW + 4 + jj * WPC, (T)0, (T)0, tag);
@@ -1007,22 +1066,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                 }
             }
 
-            // ---------------- pass 2: q = A_m D over the slab ---------------------------
-            {
-                // multi-GPU: a finished row of the partial product goes to the peers at once, so
-                // the NVLink latency overlaps the rest of the pass (see the exchange below)
-                const size_t cell = (((size_t)(tag & 1u) * G + c) * p.world) * p.qw;
-                auto send_row = [&](int idx, double v) {
-                    if (p.world > 1) {
+            // multi-GPU: a finished row of the partial product goes to the peers at once, so the
+            // NVLink latency overlaps the rest of the pass (see the exchange below)
+            const size_t cell = (((size_t)(tag & 1u) * G + c) * p.world) * p.qw;
+            auto send_row = [&](int idx, double v) {
+                if (p.world > 1) {
 #pragma unroll 1
-                        for (int pr = 0; pr < p.world; ++pr)
-                            if (pr != p.rank) ll_st_dbl(p.peer[pr] + cell + (size_t)p.rank * p.qw + idx, v, tag);
-                    }
-                };
-                if (tid == 0) {            // my l1 / err terms of this step travel with the rows
-                    send_row(rows_c, ctl->sp[2]);
-                    send_row(rows_c + 1, ctl->sp[3]);
+                    for (int pr = 0; pr < p.world; ++pr)
+                        if (pr != p.rank) ll_st_dbl(p.peer[pr] + cell + (size_t)p.rank * p.qw + idx, v, tag);
                 }
+            };
+            if (tid == 0) {                // my l1 / err terms of this step travel with the rows
+                send_row(rows_c, ctl->sp[2]);
+                send_row(rows_c + 1, ctl->sp[3]);
+            }
+
+            // ---------------- pass 2: q = A_m D over the slab ---------------------------
+            Acc accT;                      // TRANS: this thread's residual entries, all columns
+            OP::zero(accT);
+            const int ivT = TRANS ? tid % p.BXV : 0, partT = TRANS ? tid / p.BXV : 0;
+            {
                 // one row of the tile against D: partial sum of this lane's column groups
                 auto row_dot = [&](const T *trow) -> T {
                     Acc a0, a1;
@@ -1060,7 +1123,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                     if (ttrace && t2 < 16) ttrace[step * NTTRACE + 32 + t2] = globaltimer_ns();
                     const T *tile = reinterpret_cast<const T *>(ring + (size_t)slot * p.slot_bytes);
                     const int rows_t = min(TR, rows_c - t * TR);
-                    if (!(p.dbg & 4)) {
+                    if (TRANS) {
+                        // thread = (16-byte group ivT of my residual entries, column part partT)
+                        const int cols_t = min(p.TJ, p.w - t * p.TJ);
+                        if (partT < p.nparts && !(p.dbg & 4)) {
+#pragma unroll 4
+                            for (int j = partT; j < cols_t; j += p.nparts) {
+                                const VecT v = *reinterpret_cast<const VecT *>(tile + (size_t)j * p.BX + ivT * V);
+                                OP::axpy(accT, v, delta_s[t * p.TJ + j]);
+                            }
+                        }
+                    } else if (!(p.dbg & 4)) {
                         int rr = wid;
 #pragma unroll 1
                         for (; rr + NW < rows_t; rr += 2 * NW) {      // two rows per trip
@@ -1086,7 +1159,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                     if (ttrace && t2 < 16) ttrace[step * NTTRACE + 48 + t2] = globaltimer_ns();
                 }
             }
-            cbar();
+            if (TRANS) {
+                // combine the column parts through shared memory
+                T *red2 = reinterpret_cast<T *>(smem + p.off_red2);
+                if (partT < p.nparts) *reinterpret_cast<VecT *>(red2 + (size_t)partT * p.BX + ivT * V) = OP::pack(accT);
+                cbar();
+#pragma unroll 1
+                for (int i = tid; i < rows_c; i += NTC) {
+                    T sum = (T)0;
+#pragma unroll 1
+                    for (int pt = 0; pt < p.nparts; ++pt) sum += red2[(size_t)pt * p.BX + i];
+                    qpart[i] = (double)sum;
+                    send_row(i, (double)sum);
+                }
+            } else {
+                cbar();
+            }
             if (trace) trace[step * NTRACE + 8] = globaltimer_ns() - t_start;
             if (p.world > 1) {
                 // ---------------- multi-GPU: sum the partial A_m D over the ranks ----------
@@ -1098,7 +1186,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused_rowmajor(const RunPar
                 // so every rank holds bitwise the same q and the replicated r stays identical.
                 // Double-buffered by step parity: a rank can be at most one exchange ahead.
                 const int nq = rows_c + 2;
-                const size_t cell = (((size_t)(tag & 1u) * G + c) * p.world) * p.qw;
                 double *qx = reinterpret_cast<double *>(smem + p.off_qx);      // [world-1][qw]
 #pragma unroll 1
                 for (int e = tid; e < nq * (p.world - 1); e += NTC) {
@@ -1323,6 +1410,8 @@ struct b200l_ctx {
     cudaEvent_t ev0, ev1;
     // tuning
     int32_t slot_target, max_inflight, dbg;
+    CUtensorMap tmap;             // transposed layout only
+    int tmap_valid;
     // multi-GPU
     int world, rank;
     ulonglong2 *peer[B200L_MAX_WORLD];   // peer[rank] = own inbox (cudaMalloc), others IPC-mapped
@@ -1484,6 +1573,7 @@ extern "C" int b200l_ctx_bind_A(b200l_ctx *c, const void *A_dev) {
         return fail("A_dev is not a device pointer");
     c->A = A_dev;
     c->have_problem = 0;
+    c->tmap_valid = 0;
     return 0;
 }
 
@@ -1626,6 +1716,16 @@ extern "C" int b200l_reset(b200l_ctx *c) {
     return reset_state(c);
 }
 
+// warm start of the next solve from the current x and r (regularisation path): only the
+// per-sweep stop counter and the position in the cyclic block order restart
+extern "C" int b200l_restart_counters(b200l_ctx *c) {
+    if (need_A(c)) return 1;
+    if (!c->have_problem) return fail("b200l_set_problem has not been called");
+    CK(cudaMemsetAsync(c->state, 0, 64, c->stream));
+    c->step_counter = 0;
+    return 0;
+}
+
 extern "C" int b200l_set_x(b200l_ctx *c, const double *x_host) {
     if (need_A(c)) return 1;
     if (!c->have_problem) return fail("b200l_set_problem has not been called");
@@ -1688,52 +1788,91 @@ extern "C" int b200l_set_tuning(b200l_ctx *c, int32_t slot_bytes_target, int32_t
     return 0;
 }
 
-typedef void (*fused_fn)(const RunParams);
+typedef void (*fused_fn)(const RunParams, const CUtensorMap);
 
 template <typename T>
-static fused_fn pick_kernel(int cpt) {
+static fused_fn pick_kernel(int cpt, bool trans) {
+    if (trans) return lasso_fused<T, 1, true>;
     switch (cpt) {
-        case 1: return lasso_fused_rowmajor<T, 1>;
-        case 2: return lasso_fused_rowmajor<T, 2>;
-        case 4: return lasso_fused_rowmajor<T, 4>;
-        case 8: return lasso_fused_rowmajor<T, 8>;
+        case 1: return lasso_fused<T, 1, false>;
+        case 2: return lasso_fused<T, 2, false>;
+        case 4: return lasso_fused<T, 4, false>;
+        case 8: return lasso_fused<T, 8, false>;
         default: return nullptr;
     }
 }
 
 static fused_fn ctx_kernel(const b200l_ctx *c) {
-    return c->dtype == B200L_F32 ? pick_kernel<float>(c->cpt) : pick_kernel<double>(c->cpt);
+    const bool trans = c->layout == B200L_TRANSPOSED;
+    return c->dtype == B200L_F32 ? pick_kernel<float>(c->cpt, trans) : pick_kernel<double>(c->cpt, trans);
+}
+
+// tensor map of the pre-transposed matrix: 2-D (ldT residual entries, nblocks*w columns)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static int make_tensor_map(b200l_ctx *c) {
+    static encode_tiled_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled is not available");
+        encode = (encode_tiled_fn)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)c->ld, (cuuint64_t)c->nblocks * (cuuint64_t)c->brows};
+    const cuuint64_t strides[1] = {(cuuint64_t)c->ld * c->esize};
+    const cuuint32_t box[2] = {(cuuint32_t)c->geo.BX, (cuuint32_t)c->geo.TJ};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(&c->tmap, c->dtype == B200L_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+                              2, const_cast<void *>(c->A), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    c->tmap_valid = 1;
+    return 0;
 }
 
 static int plan_geometry(b200l_ctx *c) {
     if (c->geo_valid) return 0;
-    if (c->layout != B200L_ROWMAJOR)
-        return fail("the fused kernel currently supports the ROWMAJOR layout only");
+    const bool trans = c->layout == B200L_TRANSPOSED;
     RunParams &g = c->geo;
     memset(&g, 0, sizeof(g));
     const int es = (int)c->esize, V = 16 / es;
-    const int ld = (int)c->ld;
+    // columns of a block incl. padding (stride of x / d per block, width of the exchange)
+    const int ld = trans ? (int)c->xld : (int)c->ld;
     const int64_t rowbytes = (int64_t)ld * es;
-    if (rowbytes > 32768)
+    if (!trans && rowbytes > 32768)
         return fail("block width w=%d needs %lld-byte rows; the fused kernel supports rows up to 32 KiB "
                     "(use more column blocks)", c->w, (long long)rowbytes);
     const int G = std::min(c->sm_count, GMAX);
-    const int rows_max = (int)((c->N + G - 1) / G);
+    const int rows_max = trans ? V * (int)(((c->N + V - 1) / V + G - 1) / G) : (int)((c->N + G - 1) / G);
     const int ncg = ld / V;
     int cpt = 1;
-    while (cpt * NTC < ncg) cpt *= 2;
+    while (!trans && cpt * NTC < ncg) cpt *= 2;
     if (cpt > 8) return fail("internal: cpt=%d", cpt);
-    const int nrg = cpt == 1 ? std::max(1, NTC / ncg) : 1;
+    const int nrg = (!trans && cpt == 1) ? std::max(1, NTC / ncg) : 1;
     // rows per tile: as many as fit the slot target, whole quads when possible, at most 64
     int TR = (int)std::min<int64_t>(64, std::max<int64_t>(1, c->slot_target / rowbytes));
     TR = std::min(TR, (int)round_up(std::max(rows_max, 1), 4));
     if (TR >= 4) TR &= ~3;
+    // transposed layout: box of BX residual entries (odd number of 16-byte groups) x TJ columns
+    const int BXV = ((rows_max + V - 1) / V) | 1;
+    const int BX = BXV * V;
+    const int TJ = NTC;
+    const int nt_t = (c->w + TJ - 1) / TJ;
+    const int nparts = std::max(1, std::min(NTC / BXV, 32));
+    if (trans && BX > 256)
+        return fail("transposed layout: N/#SM = %d residual entries per CTA exceed the 256-element TMA box; use "
+                    "the row-major layout for N > %d", rows_max, 252 * G);
     // columns of every block owned by one CTA: a power of two (shift/mask addressing)
     int cs = 1, cs_shift = 0;
     while (cs * G < ld) { cs *= 2; ++cs_shift; }
     if (cs > MAX_CS) return fail("internal: slice width %d > %d", cs, MAX_CS);
-    const int slot_bytes = (int)round_up((int64_t)TR * rowbytes, 128);
-    const int rows_pad = (int)round_up(std::max(rows_max, 1), std::max(TR, 8));
+    const int slot_bytes = trans ? (int)round_up((int64_t)TJ * BX * es, 128) : (int)round_up((int64_t)TR * rowbytes, 128);
+    const int rows_pad = trans ? (int)round_up(BX, 8) : (int)round_up(std::max(rows_max, 1), std::max(TR, 8));
 
     int off = 0;
     auto take = [&](int bytes) { int o = off; off += (int)round_up(bytes, 128); return o; };
@@ -1746,7 +1885,8 @@ static int plan_geometry(b200l_ctx *c) {
         const int o_qT = take(rows_pad * es);
         // the step D (written after the gather, read in pass 2) overlays the row-group
         // partials (written after pass 1, read before the gather): two barriers apart
-        const int o_redT = take(nrg * 2 * ld * es);
+        const int o_redT = take(trans ? nt_t * TJ * es : nrg * 2 * ld * es);
+        const int o_red2 = take(trans ? nparts * BX * es : 16);
         const int o_delta = o_redT;
         const int o_colsum = take(2 * (4 + MAX_CS) * 16);         // gathered scalars + columns (+ group sums)
         const int o_small = take((2 * MAX_CS + 2 * NW) * 8);      // l1s, es, lsred
@@ -1756,7 +1896,7 @@ static int plan_geometry(b200l_ctx *c) {
             out->off_bar = o_bar; out->off_ctl = o_ctl; out->off_rloc = o_rloc; out->off_qloc = o_qloc;
             out->off_rT = o_rT; out->off_qT = o_qT; out->off_delta = o_delta; out->off_redT = o_redT;
             out->off_colsum = o_colsum; out->off_small = o_small; out->off_qpart = o_qpart;
-            out->off_qx = o_qx;
+            out->off_qx = o_qx; out->off_red2 = o_red2;
         }
     };
     // the ring goes first (offset 0); sized after the fixed part is known
@@ -1769,7 +1909,7 @@ static int plan_geometry(b200l_ctx *c) {
     if (S < 2)
         return fail("shared memory too small for the fused kernel: fixed=%d slot=%d optin=%d (N/SM=%d rows, "
                     "w=%d)", fixed, slot_bytes, c->smem_optin, rows_max, c->w);
-    const int nt_max = (rows_max + TR - 1) / TR;
+    const int nt_max = trans ? nt_t : (rows_max + TR - 1) / TR;
     if (S > 2 * nt_max + 2) S = 2 * nt_max + 2;   // more slots than two passes of tiles is useless
     off = 0;
     take(S * slot_bytes);
@@ -1783,8 +1923,8 @@ static int plan_geometry(b200l_ctx *c) {
     const int wpc = es / 4;
     // publishing from registers needs complete column sums per thread (one row group), a
     // column group inside one message and 32-byte aligned messages (even word count)
-    const int direct = (nrg == 1 && cs * wpc >= 4 && !(c->dbg & 128)) ? 1 : 0;
-    const int mw = direct ? ((4 + cs * wpc + 1) & ~1) : ((4 + cs * wpc) | 1);
+    const int direct = trans ? 1 : ((nrg == 1 && cs * wpc >= 4 && !(c->dbg & 128)) ? 1 : 0);
+    const int mw = (direct && !trans) ? ((4 + cs * wpc + 1) & ~1) : ((4 + cs * wpc) | 1);
     const int slot_words = slot_bytes / 16;
     int gc = G;
     if (G * mw > slot_words) {
@@ -1799,6 +1939,8 @@ static int plan_geometry(b200l_ctx *c) {
     g.ring_bytes = S * slot_bytes;
     g.nrg = nrg; g.ncg = ncg; g.rows_pad = rows_pad; g.rows_max_ = rows_max;
     g.mw = mw; g.gc = gc; g.dchunk = dchunk; g.nown = nown; g.direct_pub = direct;
+    g.BX = BX; g.BXV = BXV; g.TJ = TJ; g.nparts = nparts; g.nt_t = nt_t;
+    c->tmap_valid = 0;
     g.inflight = c->max_inflight > 0 ? std::min(c->max_inflight, S) : S;
     g.l2_ahead = (c->dbg & 8) ? 0 : 1;
     g.l2_pass = (c->dbg & 16) ? 1 : 0;
@@ -1882,7 +2024,7 @@ static int launch_fused(b200l_ctx *c, const int32_t *order_host, int64_t nsteps,
     p.N = c->N;
     p.blk_stride = c->brows * c->ld;
     p.w = c->w;
-    p.ld = (int32_t)c->ld;
+    p.ld = c->layout == B200L_TRANSPOSED ? (int32_t)c->xld : (int32_t)c->ld;
     p.nblocks = c->nblocks;
     p.x = c->x; p.d = c->d; p.drec = c->drec; p.r = c->r;
     p.gLL = c->gLL; p.dLL = c->dLL; p.abort_flag = c->abort_flag;
@@ -1906,8 +2048,9 @@ static int launch_fused(b200l_ctx *c, const int32_t *order_host, int64_t nsteps,
     for (int r = 0; r < B200L_MAX_WORLD; ++r) p.peer[r] = c->peer[r];
     p.dbg = c->dbg;
 
+    if (c->layout == B200L_TRANSPOSED && !c->tmap_valid && make_tensor_map(c)) return 1;
     fused_fn fn = ctx_kernel(c);
-    void *args[] = {(void *)&p};
+    void *args[] = {(void *)&p, (void *)&c->tmap};
     if (timed) CK(cudaEventRecord(c->ev0, c->stream));
     CK(cudaLaunchCooperativeKernel((const void *)fn, dim3(c->grid), dim3(NTHREADS), args,
                                    (size_t)c->smem_bytes, c->stream));

@@ -89,6 +89,8 @@ int b200l_gemv_n(b200l_ctx *ctx, int32_t m, const double *d_host, double *q_host
 int b200l_set_problem(b200l_ctx *ctx, const double *b_host);
 int b200l_reset(b200l_ctx *ctx);              /* x = 0, r = -b, stop counter = 0 */
 int b200l_set_x(b200l_ctx *ctx, const double *x_host);
+/* keep x and r, restart the stop counter and the cyclic block order (next mu of a path) */
+int b200l_restart_counters(b200l_ctx *ctx);
 int b200l_get_x(b200l_ctx *ctx, double *x_host);
 int b200l_get_r(b200l_ctx *ctx, double *r_host);
 

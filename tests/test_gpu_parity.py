@@ -275,3 +275,71 @@ def test_error_paths():
     solver = lasso.ClassLasso(wide, wide.diag_ATA, A, np.ones((16, 1)), 0.1, 1, 4)
     with pytest.raises(_lib.B200LassoError, match="32 KiB"):
         solver.run(SILENCE=True)
+
+
+def test_lambda_path_warm_starts_match_oracle(tmp_path):
+    """20 decreasing lambdas, each warm-started from the previous solution (BASELINE config 5
+    at oracle size): every point of the path must match the oracle run with the same x0."""
+    from convex_optimization_b200 import path as bpath
+    N, K, BLOCK = 200, 1600, 4
+    A, _, b, mu = orc.make_problem(N, K, 0.05, seed=33)
+    mus = bpath.lambda_grid(mu / 0.1, n=20)
+    assert mus[0] > mus[-1] and abs(mus[0] - 0.9 * mu / 0.1) < 1e-12
+    cal = make_gpu_cal(A, BLOCK)
+    ITER_MAX = 400 * BLOCK
+    res = bpath.lasso_path(cal, b, mus, BLOCK, ITER_MAX, 1e-5)
+    x0 = None
+    cold_iters = warm_iters = 0
+    for r, m in zip(res, mus):
+        o = orc.lasso_oracle(A, b, m, BLOCK, ITER_MAX, 1e-5, faithful=False, x0=x0)
+        assert r["iters"] == o["iters"] and r["stopped"] == o["stopped"]
+        assert np.array_equal(r["x"] != 0, o["x"] != 0)
+        assert rel(r["x"], o["x"]) < TOL["double"] or np.abs(o["x"]).max() == 0
+        assert abs(r["objective"] - o["objective"]) <= 1e-10 * max(1.0, abs(o["objective"]))
+        x0 = o["x"]
+        warm_iters += o["iters"]
+        cold_iters += orc.lasso_oracle(A, b, m, BLOCK, ITER_MAX, 1e-5, faithful=False)["iters"]
+    assert warm_iters < cold_iters                    # warm starts pay
+    nnz = [int(np.count_nonzero(r["x"])) for r in res]
+    assert nnz[0] <= nnz[-1]                          # the support grows along the path
+
+
+def test_traces_written_for_compare_py(tmp_path):
+    from convex_optimization_b200 import path as bpath
+    g, A, b, mu = load_golden("g_128x512_b2_p4")
+    solver, err_iter, time_iter, _ = run_fused("ClassLasso", A, b, mu, 2, int(g["ITER_MAX"]), float(g["ERR_BOUND"]))
+    pt, pe = bpath.save_traces("GPU", time_iter, err_iter, solver.iters, directory=str(tmp_path))
+    t, e = np.loadtxt(pt), np.loadtxt(pe)
+    assert t.shape == e.shape and len(t) == solver.iters
+    assert np.all(np.diff(t) >= 0) and np.all(e > 0)
+    assert np.all(np.isfinite(np.log10(e)))           # what compare.py:12-13 computes
+
+
+@pytest.mark.parametrize("TYPE", ["double", "float"])
+@pytest.mark.parametrize("shape", [(300, 2400, 4, 0.05), (257, 1002, 3, 0.05), (1000, 4000, 2, 0.02),
+                                   (33, 70, 5, 0.2), (2000, 3000, 1, 0.02)])
+def test_fused_transposed_layout_vs_oracle(shape, TYPE):
+    """the pre-transposed (BLOCK, w, N) layout through the fused kernel (2-D TMA boxes)"""
+    from convex_optimization_b200 import lasso
+    N, K, BLOCK, den = shape
+    A, _, b, mu = orc.make_problem(N, K, den, seed=N + K + 1)
+    if TYPE == "float":
+        A = A.astype(np.float32).astype(np.float64)
+    ITER_MAX = 60 * BLOCK if TYPE == "double" else 10 * BLOCK
+    bound = 1e-4 if TYPE == "double" else None          # fp32: fixed iteration count
+    o = orc.lasso_oracle(A, b, mu, BLOCK, ITER_MAX, bound, faithful=False)
+    cal = make_gpu_cal(A, BLOCK, TYPE, LAYOUT="transposed")
+    solver = lasso.ClassLasso(cal, cal.diag_ATA, A, b, mu, BLOCK, ITER_MAX)
+    err_iter = np.zeros(ITER_MAX)
+    solver.run(bound, err_iter=err_iter, SILENCE=True)
+    assert solver.iters == o["iters"] and solver.stopped == o["stopped"]
+    if TYPE == "double":
+        assert np.array_equal(solver.x != 0, o["x"] != 0)
+    assert rel(solver.x, o["x"]) < TOL[TYPE]
+    assert abs(orc.objective(A, b, solver.x, mu) - o["objective"]) / o["objective"] < TOL[TYPE]
+    assert np.abs(err_iter[:o["iters"]] - o["err"]).max() < max(TOL[TYPE], 1e-10)
+    # and the row-major run of the same instance gives the same iterates
+    cal2 = make_gpu_cal(A, BLOCK, TYPE, LAYOUT="row")
+    s2 = lasso.ClassLasso(cal2, cal2.diag_ATA, A, b, mu, BLOCK, ITER_MAX)
+    s2.run(bound, SILENCE=True)
+    assert s2.iters == solver.iters and rel(s2.x, solver.x) < TOL[TYPE]
