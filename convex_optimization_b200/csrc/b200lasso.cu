@@ -649,7 +649,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
             rg = 0;
         }
         // pass-2 mapping: warp = rows wid, wid+NW, .. of a tile; lane = column groups lane+32k
-        const int dk_n = (ncg + 31) >> 5;
+        int cgc[DK > 0 ? DK : 1];            // element offset of this lane's k-th column group
+#pragma unroll
+        for (int k = 0; k < (DK > 0 ? DK : 1); ++k) cgc[k] = min(lane + 32 * k, ncg - 1) * V;
         // stage-2 mapping: thread jl < cs owns column j0+jl of every block
         const int j0 = c * cs;
         const int jcol = j0 + tid;
@@ -717,7 +719,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                         if (TR >= 4) {
                             // whole quads: rows past rows_t hold finite stale data and meet r = q = 0
                             const int nquad = (rows_t + 3) >> 2;
-#pragma unroll 1
+#pragma unroll 2
                             for (int q4 = rg; q4 < nquad; q4 += nrg) {
                                 T rv[4], qv[4];
                                 load4(rTt + 4 * q4, rv);
@@ -1092,16 +1094,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                     OP::zero(a0);
                     OP::zero(a1);
                     if (DK > 0) {
+                        // branch-free on purpose (clamped addresses, dreg is 0 past ncg): all the
+                        // loads of a row are in flight before the first multiply
+                        VecT v[DK > 0 ? DK : 1];
+#pragma unroll
+                        for (int k = 0; k < DK; ++k)
+                            v[k] = *reinterpret_cast<const VecT *>(trow + cgc[k]);
 #pragma unroll
                         for (int k = 0; k < DK; k += 2) {
-                            if (k < dk_n) {
-                                const int cga = min(lane + 32 * k, ncg - 1);          // dreg is 0 past ncg
-                                const int cgb = min(lane + 32 * (k + 1), ncg - 1);
-                                const VecT va = *reinterpret_cast<const VecT *>(trow + cga * V);
-                                const VecT vb = *reinterpret_cast<const VecT *>(trow + cgb * V);
-                                OP::mac(a0, va, dreg[k]);
-                                OP::mac(a1, vb, dreg[k + 1 < DK ? k + 1 : k]);
-                            }
+                            OP::mac(a0, v[k], dreg[k]);
+                            OP::mac(a1, v[k + 1 < DK ? k + 1 : k], dreg[k + 1 < DK ? k + 1 : k]);
                         }
                     } else {
 #pragma unroll 2
