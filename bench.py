@@ -250,6 +250,10 @@ def main_gpu(args):
     cfg = dict(C2)
     if args.small:
         cfg.update(N=2000, K=20000, BLOCK=20)
+    if args.config == "c3":       # BASELINE.json configs[2]: fp64 20,000 x 200,000 (32 GB), not the bench line
+        cfg.update(N=20000, K=200000, BLOCK=100, dtype="double", seed=3)
+    elif args.config == "c4shard":  # one GPU's share of configs[3] on 8 GPUs: 50,000 x 125,000 fp32 (25 GB)
+        cfg.update(N=50000, K=125000, BLOCK=100, dtype="float", seed=4)
     N, K, BLOCK = cfg["N"], cfg["K"], cfg["BLOCK"]
     s = 4 if cfg["dtype"] == "float" else 8
     layout = args.layout
@@ -271,6 +275,8 @@ def main_gpu(args):
     if args.slot_bytes or args.inflight:
         cal.set_tuning(args.slot_bytes, args.inflight)
     lib, ctx = cal._lib, cal.ctx
+    if args.dbg:
+        _lib.check(lib.b200l_debug_flags(ctx, args.dbg))
     # the library launches on the stream the CUDA events below are recorded on
     stream = torch.cuda.current_stream(device)
     _lib.check(lib.b200l_ctx_set_stream(ctx, ctypes.c_void_p(stream.cuda_stream)))
@@ -407,6 +413,9 @@ def main():
     ap.add_argument("--e2e-sweeps", type=int, default=5)
     ap.add_argument("--slot-bytes", type=int, default=0)
     ap.add_argument("--inflight", type=int, default=0)
+    ap.add_argument("--dbg", type=int, default=0, help="diagnostic flags of b200l_debug_flags (not for bench values)")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4shard"],
+                    help="c2 is the bench workload; the others are reported in DESIGN.md only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

