@@ -318,7 +318,8 @@ struct RunParams {
     int32_t TR, S, slot_bytes, cs, cs_shift, nrg, ncg, rows_pad, rows_max_, inflight, l2_ahead, l2_pass;
     // multi-GPU: rank `rank` of `world` holds column slice `rank` of every block; peer[r] is the
     // q-inbox of rank r: [2 parities][G CTAs][world sources][qw] words (peer[rank] is local)
-    int32_t world, rank, qw;
+    int32_t xmode;            // cross-rank exchange: 0 per-tile sends + bulk-copy gather, 1 per-row sends + polled gather
+    int32_t world, rank, qw, qx_words;   // qx_words: the cell of a step fits the landing area
     ulonglong2 *peer[B200L_MAX_WORLD];
     int32_t direct_pub;       // partial gradients are published from registers (one row group)
     int32_t gate_mode;        // 0: re-stream freely, 1/2/3: after inbox fetch issued / gather done / D fetch issued
@@ -328,7 +329,7 @@ struct RunParams {
     int32_t mw, gc, dchunk, nown;   // message words, sources per gather group, D words per fetch, owner CTAs
     // shared-memory offsets
     int32_t off_bar, off_ctl, off_rloc, off_qloc, off_rT, off_qT, off_delta, off_redT, off_colsum,
-        off_small, off_qpart, off_qx, ring_bytes;
+        off_small, off_qpart, off_qx, off_tilecnt, ring_bytes;
 };
 
 // bounded spinning: returns false when the wait has to be abandoned (a peer timed out or
@@ -486,6 +487,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
     double *es = l1s + MAX_CS;
     double *lsred = l1s + 2 * MAX_CS;     // [2][NW] line-search partials of the warps
     double *qpart = reinterpret_cast<double *>(smem + p.off_qpart);       // [rows] A_m D
+    int *tilecnt = reinterpret_cast<int *>(smem + p.off_tilecnt);         // warps done with a pass-2 tile
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int c = blockIdx.x, G = gridDim.x;
@@ -516,6 +518,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
         ctl->stop = 0;
         ctl->abort = 0;
         ctl->gate = 0;
+        for (int i = 0; i < 128; ++i) tilecnt[i] = 0;
         ctl->kc = 0;
         ctl->k_issued = 0;
         fence_mbar_init();
@@ -649,9 +652,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
             rg = 0;
         }
         // pass-2 mapping: warp = rows wid, wid+NW, .. of a tile; lane = column groups lane+32k
-        int cgc[DK > 0 ? DK : 1];            // element offset of this lane's k-th column group
-#pragma unroll
-        for (int k = 0; k < (DK > 0 ? DK : 1); ++k) cgc[k] = min(lane + 32 * k, ncg - 1) * V;
+        const int dk_n = (ncg + 31) >> 5;
         // stage-2 mapping: thread jl < cs owns column j0+jl of every block
         const int j0 = c * cs;
         const int jcol = j0 + tid;
@@ -719,7 +720,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                         if (TR >= 4) {
                             // whole quads: rows past rows_t hold finite stale data and meet r = q = 0
                             const int nquad = (rows_t + 3) >> 2;
-#pragma unroll 2
+#pragma unroll 1
                             for (int q4 = rg; q4 < nquad; q4 += nrg) {
                                 T rv[4], qv[4];
                                 load4(rTt + 4 * q4, rv);
@@ -1084,6 +1085,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
             }
 
             // ---------------- pass 2: q = A_m D over the slab ---------------------------
+            int hold2 = -1;                // multi-GPU: ring slot of the last pass-2 tile, held for the exchange
             Acc accT;                      // TRANS: this thread's residual entries, all columns
             OP::zero(accT);
             const int ivT = TRANS ? tid % p.BXV : 0, partT = TRANS ? tid / p.BXV : 0;
@@ -1094,16 +1096,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                     OP::zero(a0);
                     OP::zero(a1);
                     if (DK > 0) {
-                        // branch-free on purpose (clamped addresses, dreg is 0 past ncg): all the
-                        // loads of a row are in flight before the first multiply
-                        VecT v[DK > 0 ? DK : 1];
-#pragma unroll
-                        for (int k = 0; k < DK; ++k)
-                            v[k] = *reinterpret_cast<const VecT *>(trow + cgc[k]);
 #pragma unroll
                         for (int k = 0; k < DK; k += 2) {
-                            OP::mac(a0, v[k], dreg[k]);
-                            OP::mac(a1, v[k + 1 < DK ? k + 1 : k], dreg[k + 1 < DK ? k + 1 : k]);
+                            if (k < dk_n) {
+                                const int cga = min(lane + 32 * k, ncg - 1);          // dreg is 0 past ncg
+                                const int cgb = min(lane + 32 * (k + 1), ncg - 1);
+                                const VecT va = *reinterpret_cast<const VecT *>(trow + cga * V);
+                                const VecT vb = *reinterpret_cast<const VecT *>(trow + cgb * V);
+                                OP::mac(a0, va, dreg[k]);
+                                OP::mac(a1, vb, dreg[k + 1 < DK ? k + 1 : k]);
+                            }
                         }
                     } else {
 #pragma unroll 2
@@ -1145,19 +1147,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                             if ((lane & 15) == 0) {
                                 const int row = t * TR + rr + (lane >> 4) * NW;
                                 qpart[row] = (double)qs;
-                                send_row(row, (double)qs);
+                                if (p.xmode == 1) send_row(row, (double)qs);
                             }
                         }
                         if (rr < rows_t) {
                             const T qs = warp_sum(row_dot(tile + (size_t)rr * ld));
                             if (lane == 0) {
                                 qpart[t * TR + rr] = (double)qs;
-                                send_row(t * TR + rr, (double)qs);
+                                if (p.xmode == 1) send_row(t * TR + rr, (double)qs);
+                            }
+                        }
+                        if (p.world > 1 && p.xmode == 0) {
+                            // multi-GPU: the warp that completes a tile sends its rows to every peer,
+                            // consecutive lanes = consecutive words (whole NVLink packets), while the
+                            // other warps go on with the next tile
+                            __syncwarp();
+                            int last = 0;
+                            if (nt > 128) {            // more tiles than counters: every warp sends its own rows
+                                if (lane == 0)
+                                    for (int r2 = wid; r2 < rows_t; r2 += NW) send_row(t * TR + r2, qpart[t * TR + r2]);
+                            } else if (lane == 0) {
+                                __threadfence_block();
+                                last = atomicAdd(tilecnt + (t2 & 127), 1) == NW - 1;
+                            }
+                            last = __shfl_sync(0xffffffffu, last, 0);
+                            if (last) {
+                                __threadfence_block();
+#pragma unroll 1
+                                for (int i = lane; i < rows_t; i += 32) send_row(t * TR + i, qpart[t * TR + i]);
+                                if (lane == 0) tilecnt[t2 & 127] = 0;
                             }
                         }
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(empty + slot);
+                    if (p.qx_words && t2 == nt - 1) hold2 = slot;      // landing area of the rank exchange
+                    else if (lane == 0) mbar_arrive(empty + slot);
                     if (ttrace && t2 < 16) ttrace[step * NTTRACE + 48 + t2] = globaltimer_ns();
                 }
             }
@@ -1188,32 +1212,79 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                 // so every rank holds bitwise the same q and the replicated r stays identical.
                 // Double-buffered by step parity: a rank can be at most one exchange ahead.
                 const int nq = rows_c + 2;
-                double *qx = reinterpret_cast<double *>(smem + p.off_qx);      // [world-1][qw]
+                const ulonglong2 *mycell = p.peer[p.rank] + cell;              // [world][qw] words
+                if (p.qx_words) {
+                    // the whole cell (all sources, contiguous) comes in by one bulk copy; threads
+                    // check the tags, poll a missing word in L2, and the copy is repeated
+                    // ... into the ring slot of the last pass-2 tile (slot 0 when this CTA has no rows)
+                    ulonglong2 *qxw = reinterpret_cast<ulonglong2 *>(ring + (size_t)(hold2 >= 0 ? hold2 : 0) * p.slot_bytes);
+                    const int nwords = p.world * p.qw;
+                    for (;;) {
+                        if (tid == 0) {
+                            mbar_expect_tx(xbar, (uint32_t)nwords * 16u);
+                            tma_bulk_g2s(qxw, mycell, (uint32_t)nwords * 16u, xbar);
+                        }
+                        mbar_wait(xbar, xphase);
+                        xphase ^= 1u;
+                        int bad = -1;
 #pragma unroll 1
-                for (int e = tid; e < nq * (p.world - 1); e += NTC) {
-                    const int k = e / nq, i = e - k * nq;
-                    const int sr = k < p.rank ? k : k + 1;
-                    const ulonglong2 *wp = p.peer[p.rank] + cell + (size_t)sr * p.qw + i;
-                    ulonglong2 w = ll_ld(wp);
-                    waiter.begin(((long long)step << 32) | (1LL << 30) | (long long)(sr * 65536 + i));
-                    while (!ll_ok(w, tag) && !(p.dbg & 1)) {
-                        if (!waiter.again()) break;
-                        w = ll_ld(wp);
+                        for (int e = tid; e < nq * p.world; e += NTC) {
+                            const int sr = e / nq, i = e - sr * nq;
+                            if (sr != p.rank && !ll_ok(qxw[sr * p.qw + i], tag)) bad = sr * p.qw + i;
+                        }
+                        if (!cbar_or(bad >= 0) || (p.dbg & 1)) break;
+                        if (bad >= 0) {
+                            waiter.begin(((long long)step << 32) | (1LL << 30) | (long long)bad);
+                            while (!ll_ok(ll_ld(mycell + bad), tag)) {
+                                if (!waiter.again()) break;
+                            }
+                        }
+                        if (cbar_or(*(volatile int *)&ctl->abort != 0)) break;
                     }
-                    qx[k * p.qw + i] = ll_dbl(w);
-                }
-                cbar();
 #pragma unroll 1
-                for (int i = tid; i < nq; i += NTC) {
-                    const double own = i < rows_c ? qpart[i] : ctl->sp[2 + (i - rows_c)];
-                    double acc = 0.0;
+                    for (int i = tid; i < nq; i += NTC) {
+                        const double own = i < rows_c ? qpart[i] : ctl->sp[2 + (i - rows_c)];
+                        double acc = 0.0;
 #pragma unroll 1
-                    for (int sr = 0; sr < p.world; ++sr) {
-                        const double v = sr == p.rank ? own : qx[(sr < p.rank ? sr : sr - 1) * p.qw + i];
-                        acc = (i == rows_c + 1) ? fmax(acc, v) : acc + v;
+                        for (int sr = 0; sr < p.world; ++sr) {
+                            const double v = sr == p.rank ? own : ll_dbl(qxw[sr * p.qw + i]);
+                            acc = (i == rows_c + 1) ? fmax(acc, v) : acc + v;
+                        }
+                        if (i < rows_c) qpart[i] = acc;
+                        else ctl->sp[2 + (i - rows_c)] = acc;
                     }
-                    if (i < rows_c) qpart[i] = acc;
-                    else ctl->sp[2 + (i - rows_c)] = acc;
+                    if (hold2 >= 0) {              // the landing area goes back to the producer
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(empty + hold2);
+                    }
+                } else {
+                    double *qx = reinterpret_cast<double *>(smem + p.off_qx);  // [world-1][qw]
+#pragma unroll 1
+                    for (int e = tid; e < nq * (p.world - 1); e += NTC) {
+                        const int k = e / nq, i = e - k * nq;
+                        const int sr = k < p.rank ? k : k + 1;
+                        const ulonglong2 *wp = mycell + (size_t)sr * p.qw + i;
+                        ulonglong2 w = ll_ld(wp);
+                        waiter.begin(((long long)step << 32) | (1LL << 30) | (long long)(sr * 65536 + i));
+                        while (!ll_ok(w, tag) && !(p.dbg & 1)) {
+                            if (!waiter.again()) break;
+                            w = ll_ld(wp);
+                        }
+                        qx[k * p.qw + i] = ll_dbl(w);
+                    }
+                    cbar();
+#pragma unroll 1
+                    for (int i = tid; i < nq; i += NTC) {
+                        const double own = i < rows_c ? qpart[i] : ctl->sp[2 + (i - rows_c)];
+                        double acc = 0.0;
+#pragma unroll 1
+                        for (int sr = 0; sr < p.world; ++sr) {
+                            const double v = sr == p.rank ? own : qx[(sr < p.rank ? sr : sr - 1) * p.qw + i];
+                            acc = (i == rows_c + 1) ? fmax(acc, v) : acc + v;
+                        }
+                        if (i < rows_c) qpart[i] = acc;
+                        else ctl->sp[2 + (i - rows_c)] = acc;
+                    }
                 }
             }
             {
@@ -1896,12 +1967,20 @@ static int plan_geometry(b200l_ctx *c) {
         const int o_colsum = take(2 * (4 + MAX_CS) * 16);         // gathered scalars + columns (+ group sums)
         const int o_small = take((2 * MAX_CS + 2 * NW) * 8);      // l1s, es, lsred
         const int o_qpart = take(rows_pad * 8);
-        const int o_qx = take(c->world > 1 ? (c->world - 1) * (int)round_up(rows_max + 2, 2) * 8 : 16);
+        const int qw_plan = (int)round_up(rows_max + 2, 2);
+        const int cell_bytes = c->world * qw_plan * 16;         // raw words of one exchange step
+        // few words to collect (at most one per thread): per-row sends and a polled gather are
+        // quicker than per-tile sends and a bulk-copy gather (dbg bits 8/9 force either)
+        const bool few = (c->world - 1) * (rows_max + 2) <= NTC;
+        const bool cell_in_slot = c->world > 1 && cell_bytes <= slot_bytes && !(c->dbg & 256) && (!few || (c->dbg & 512));
+        const int o_qx = take(c->world > 1 && !cell_in_slot ? (c->world - 1) * qw_plan * 8 : 16);
+        const int o_tilecnt = take(128 * 4);
         if (out) {
             out->off_bar = o_bar; out->off_ctl = o_ctl; out->off_rloc = o_rloc; out->off_qloc = o_qloc;
             out->off_rT = o_rT; out->off_qT = o_qT; out->off_delta = o_delta; out->off_redT = o_redT;
             out->off_colsum = o_colsum; out->off_small = o_small; out->off_qpart = o_qpart;
-            out->off_qx = o_qx; out->off_red2 = o_red2;
+            out->off_qx = o_qx; out->off_red2 = o_red2; out->off_tilecnt = o_tilecnt;
+            out->qx_words = cell_in_slot ? c->world * qw_plan : 0;
         }
     };
     // the ring goes first (offset 0); sized after the fixed part is known
@@ -2053,6 +2132,8 @@ static int launch_fused(b200l_ctx *c, const int32_t *order_host, int64_t nsteps,
     p.world = c->world;
     p.rank = c->rank;
     p.qw = c->world > 1 ? (int32_t)round_up(c->geo.rows_max_ + 2, 2) : 0;
+    p.qx_words = c->geo.qx_words;
+    p.xmode = c->geo.qx_words ? 0 : 1;
     for (int r = 0; r < B200L_MAX_WORLD; ++r) p.peer[r] = c->peer[r];
     p.dbg = c->dbg;
 
