@@ -12,7 +12,8 @@ import sys
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, "libb200lasso.so")
+# B200L_LIB selects another build of the same source (diagnostics, e.g. -DB200L_LEAN)
+LIB_PATH = os.environ.get("B200L_LIB") or os.path.join(_PKG, "libb200lasso.so")
 SRC = os.path.join(_PKG, "csrc", "b200lasso.cu")
 INCLUDE = os.path.join(_ROOT, "include")
 HEADER = os.path.join(INCLUDE, "b200lasso.h")

@@ -461,7 +461,10 @@ __device__ __forceinline__ T warp_sum_pair(const T a, const T b, const int lane)
 //       block is then a 2-D box (all columns x its residual entries), fetched tile by tile
 //       through a tensor map.  Pass 1 is a row-dot per column (thread = column), pass 2 an
 //       axpy over columns (thread = (16-byte group of residual entries, column part)).
-template <typename T, int CPT, bool TRANS>
+// FULL : with the multi-GPU exchange, the phase / tile tracing and the diagnostic switches.  The
+//       plain single-GPU solve runs the FULL = false instantiation: the per-step code has to
+//       stay resident in the instruction cache and every rarely used branch costs footprint.
+template <typename T, int CPT, bool TRANS, bool FULL>
 __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, const __grid_constant__ CUtensorMap tmap) {
     using VecT = typename VT<T>::type;
     using LL = LLW<T>;
@@ -470,6 +473,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
     constexpr int V = VT<T>::V;
     constexpr int WPC = LL::WPC;
     constexpr int DK = CPT == 1 ? NTC / 32 : 0;
+    const int WORLD = FULL ? p.world : 1, DBG = FULL ? p.dbg : 0;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *ring = smem;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + p.off_bar);
@@ -591,7 +595,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                             // slab for pass 2 (L2 hits), pull the slab of the next step into L2
                             if (pass == 1 - p.l2_pass && An) tma_prefetch_l2(An + (size_t)t * tile_bytes, bytes);
                         }
-                        if (p.ttrace && t < 16)
+                        if (FULL && p.ttrace && t < 16)
                             p.ttrace[((size_t)c * p.nsteps + step) * NTTRACE + 64 + pass * 16 + t] = globaltimer_ns();
                         cur.advance(S);
                         ++k;
@@ -634,9 +638,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
         const ulonglong2 *inbox = p.gLL + (size_t)c * G * p.mw;
         Waiter waiter{p.abort_flag, &ctl->abort, p.wait_limit_ns, 0u, 0ull, p.state + 4, 0};
         unsigned long long *trace =
-            (p.trace != nullptr && tid == 0) ? p.trace + (size_t)c * p.nsteps * NTRACE : nullptr;
+            (FULL && p.trace != nullptr && tid == 0) ? p.trace + (size_t)c * p.nsteps * NTRACE : nullptr;
         unsigned long long *ttrace =
-            (p.ttrace != nullptr && tid == 0) ? p.ttrace + (size_t)c * p.nsteps * NTTRACE : nullptr;
+            (FULL && p.ttrace != nullptr && tid == 0) ? p.ttrace + (size_t)c * p.nsteps * NTTRACE : nullptr;
         int mc = (int)(p.step0 % p.nblocks);
 
         // pass-1 mapping: thread = (column group cg0 [+k*NTC], row group rg of nrg)
@@ -702,7 +706,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                         Acc a0, a1;
                         OP::zero(a0);
                         OP::zero(a1);
-                        if (j < p.w && !(p.dbg & 2)) {
+                        if (j < p.w && !(DBG & 2)) {
                             const T *col = tile + (size_t)tid * p.BX;
 #pragma unroll 4
                             for (int iv = 0; iv < p.BXV; ++iv) {
@@ -716,7 +720,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                             const int jj = j & (cs - 1);
                             LL::put(p.gLL + ((size_t)rd * G + c) * p.mw + 4 + jj * WPC, OP::hsum(a0), OP::hsum(a1), tag);
                         }
-                    } else if (p1_active && !(p.dbg & 2)) {
+                    } else if (p1_active && !(DBG & 2)) {
                         if (TR >= 4) {
                             // whole quads: rows past rows_t hold finite stale data and meet r = q = 0
                             const int nquad = (rows_t + 3) >> 2;
@@ -856,6 +860,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                     const int gn = min(p.gc, G - g0);
                     const ulonglong2 *srcw = inbox + (size_t)g0 * MW;
                     const int nwords = gn * MW;
+                    int nfetch = 0;
                     for (;;) {
                         if (tid == 0) {
                             mbar_expect_tx(xbar, (uint32_t)nwords * 16u);
@@ -864,11 +869,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                         }
                         mbar_wait(xbar, xphase);
                         xphase ^= 1u;
+                        if (trace && !drain && nfetch == 0) trace[step * NTRACE + 10] = globaltimer_ns() - t_start;
+                        ++nfetch;
+                        if (trace && !drain) trace[step * NTRACE + 11] = nfetch;
                         int bad = -1;
-#pragma unroll 4
+#pragma unroll 2
                         for (int e = tid; e < nwords; e += NTC)
                             if (!ll_ok(stage[e], tag)) bad = e;
-                        if (!cbar_or(bad >= 0) || (p.dbg & 1)) break;
+                        if (!cbar_or(bad >= 0) || (DBG & 1)) break;
                         if (bad >= 0) {
                             waiter.begin(((long long)step << 32) | ((long long)(g0 * MW + bad) & 0xffffffff));
                             while (!ll_ok(ll_ld(srcw + bad), tag)) {
@@ -885,24 +893,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             const int vc = vc0 + h * NW;
-                            if (vc < nvc) {
-                                const int wi = vc < 4 ? vc : 4 + (vc - 4) * WPC;
+                            // one code path for scalars (a double in word vc) and columns: a word
+                            // yields (va, vb); only the decoding differs, selected per warp
+                            const bool is_s = vc < 4, is_max = vc == 3;
+                            const int wi = is_s ? vc : 4 + (vc - 4) * WPC;
+                            const ulonglong2 *wp = stage + (vc < nvc ? wi : 0) + lane * MW;
 #pragma unroll
-                                for (int i = 0; i < PPL; ++i) {
-                                    const int pp = lane + 32 * i;
-                                    if (pp < gn) {
-                                        const ulonglong2 w0 = stage[pp * MW + wi];
-                                        if (vc < 4) {
-                                            const double sv = ll_dbl(w0);
-                                            acc[h][0] = vc == 3 ? fmax(acc[h][0], sv) : acc[h][0] + sv;
-                                        } else if (WPC == 1) {
-                                            acc[h][0] += (double)__uint_as_float((uint32_t)w0.x);
-                                            acc[h][1] += (double)__uint_as_float((uint32_t)w0.y);
-                                        } else {
-                                            acc[h][0] += ll_dbl(w0);
-                                            acc[h][1] += ll_dbl(stage[pp * MW + wi + 1]);
-                                        }
+                            for (int i = 0; i < PPL; ++i) {
+                                if (vc < nvc && lane + 32 * i < gn) {
+                                    const ulonglong2 w0 = wp[i * 32 * MW];
+                                    double va, vb;
+                                    if (WPC == 1) {
+                                        va = is_s ? ll_dbl(w0) : (double)__uint_as_float((uint32_t)w0.x);
+                                        vb = is_s ? 0.0 : (double)__uint_as_float((uint32_t)w0.y);
+                                    } else {
+                                        va = ll_dbl(w0);
+                                        vb = is_s ? 0.0 : ll_dbl(wp[i * 32 * MW + 1]);
                                     }
+                                    acc[h][0] = is_max ? fmax(acc[h][0], va) : acc[h][0] + va;
+                                    acc[h][1] += vb;
                                 }
                             }
                         }
@@ -1018,7 +1027,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
 #pragma unroll 4
                         for (int e = tid; e < nwords; e += NTC)
                             if (!ll_ok(stage[e], tag)) bad = e;
-                        if (!cbar_or(bad >= 0) || (p.dbg & 1)) break;
+                        if (!cbar_or(bad >= 0) || (DBG & 1)) break;
                         if (bad >= 0) {
                             waiter.begin(((long long)step << 32) | (1LL << 31) | (long long)(w0 + bad));
                             while (!ll_ok(ll_ld(srcw + bad), tag)) {
@@ -1071,11 +1080,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
 
             // multi-GPU: a finished row of the partial product goes to the peers at once, so the
             // NVLink latency overlaps the rest of the pass (see the exchange below)
-            const size_t cell = (((size_t)(tag & 1u) * G + c) * p.world) * p.qw;
+            const size_t cell = (((size_t)(tag & 1u) * G + c) * WORLD) * p.qw;
             auto send_row = [&](int idx, double v) {
-                if (p.world > 1) {
+                if (WORLD > 1) {
 #pragma unroll 1
-                    for (int pr = 0; pr < p.world; ++pr)
+                    for (int pr = 0; pr < WORLD; ++pr)
                         if (pr != p.rank) ll_st_dbl(p.peer[pr] + cell + (size_t)p.rank * p.qw + idx, v, tag);
                 }
             };
@@ -1130,14 +1139,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                     if (TRANS) {
                         // thread = (16-byte group ivT of my residual entries, column part partT)
                         const int cols_t = min(p.TJ, p.w - t * p.TJ);
-                        if (partT < p.nparts && !(p.dbg & 4)) {
+                        if (partT < p.nparts && !(DBG & 4)) {
 #pragma unroll 4
                             for (int j = partT; j < cols_t; j += p.nparts) {
                                 const VecT v = *reinterpret_cast<const VecT *>(tile + (size_t)j * p.BX + ivT * V);
                                 OP::axpy(accT, v, delta_s[t * p.TJ + j]);
                             }
                         }
-                    } else if (!(p.dbg & 4)) {
+                    } else if (!(DBG & 4)) {
                         int rr = wid;
 #pragma unroll 1
                         for (; rr + NW < rows_t; rr += 2 * NW) {      // two rows per trip
@@ -1157,7 +1166,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                                 if (p.xmode == 1) send_row(t * TR + rr, (double)qs);
                             }
                         }
-                        if (p.world > 1 && p.xmode == 0) {
+                        if (WORLD > 1 && p.xmode == 0) {
                             // multi-GPU: the warp that completes a tile sends its rows to every peer,
                             // consecutive lanes = consecutive words (whole NVLink packets), while the
                             // other warps go on with the next tile
@@ -1180,7 +1189,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                         }
                     }
                     __syncwarp();
-                    if (p.qx_words && t2 == nt - 1) hold2 = slot;      // landing area of the rank exchange
+                    if (FULL && p.qx_words && t2 == nt - 1) hold2 = slot;      // landing area of the rank exchange
                     else if (lane == 0) mbar_arrive(empty + slot);
                     if (ttrace && t2 < 16) ttrace[step * NTTRACE + 48 + t2] = globaltimer_ns();
                 }
@@ -1202,7 +1211,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                 cbar();
             }
             if (trace) trace[step * NTRACE + 8] = globaltimer_ns() - t_start;
-            if (p.world > 1) {
+            if (WORLD > 1) {
                 // ---------------- multi-GPU: sum the partial A_m D over the ranks ----------
                 // (the reduce of lasso.py:126 over the reference's P column slices).  CTA c of
                 // every rank owns the same rows; during pass 2 it stored its rows_c partial sums
@@ -1218,7 +1227,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                     // check the tags, poll a missing word in L2, and the copy is repeated
                     // ... into the ring slot of the last pass-2 tile (slot 0 when this CTA has no rows)
                     ulonglong2 *qxw = reinterpret_cast<ulonglong2 *>(ring + (size_t)(hold2 >= 0 ? hold2 : 0) * p.slot_bytes);
-                    const int nwords = p.world * p.qw;
+                    const int nwords = WORLD * p.qw;
                     for (;;) {
                         if (tid == 0) {
                             mbar_expect_tx(xbar, (uint32_t)nwords * 16u);
@@ -1228,11 +1237,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                         xphase ^= 1u;
                         int bad = -1;
 #pragma unroll 1
-                        for (int e = tid; e < nq * p.world; e += NTC) {
+                        for (int e = tid; e < nq * WORLD; e += NTC) {
                             const int sr = e / nq, i = e - sr * nq;
                             if (sr != p.rank && !ll_ok(qxw[sr * p.qw + i], tag)) bad = sr * p.qw + i;
                         }
-                        if (!cbar_or(bad >= 0) || (p.dbg & 1)) break;
+                        if (!cbar_or(bad >= 0) || (DBG & 1)) break;
                         if (bad >= 0) {
                             waiter.begin(((long long)step << 32) | (1LL << 30) | (long long)bad);
                             while (!ll_ok(ll_ld(mycell + bad), tag)) {
@@ -1246,7 +1255,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                         const double own = i < rows_c ? qpart[i] : ctl->sp[2 + (i - rows_c)];
                         double acc = 0.0;
 #pragma unroll 1
-                        for (int sr = 0; sr < p.world; ++sr) {
+                        for (int sr = 0; sr < WORLD; ++sr) {
                             const double v = sr == p.rank ? own : ll_dbl(qxw[sr * p.qw + i]);
                             acc = (i == rows_c + 1) ? fmax(acc, v) : acc + v;
                         }
@@ -1260,13 +1269,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                 } else {
                     double *qx = reinterpret_cast<double *>(smem + p.off_qx);  // [world-1][qw]
 #pragma unroll 1
-                    for (int e = tid; e < nq * (p.world - 1); e += NTC) {
+                    for (int e = tid; e < nq * (WORLD - 1); e += NTC) {
                         const int k = e / nq, i = e - k * nq;
                         const int sr = k < p.rank ? k : k + 1;
                         const ulonglong2 *wp = mycell + (size_t)sr * p.qw + i;
                         ulonglong2 w = ll_ld(wp);
                         waiter.begin(((long long)step << 32) | (1LL << 30) | (long long)(sr * 65536 + i));
-                        while (!ll_ok(w, tag) && !(p.dbg & 1)) {
+                        while (!ll_ok(w, tag) && !(DBG & 1)) {
                             if (!waiter.again()) break;
                             w = ll_ld(wp);
                         }
@@ -1278,7 +1287,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                         const double own = i < rows_c ? qpart[i] : ctl->sp[2 + (i - rows_c)];
                         double acc = 0.0;
 #pragma unroll 1
-                        for (int sr = 0; sr < p.world; ++sr) {
+                        for (int sr = 0; sr < WORLD; ++sr) {
                             const double v = sr == p.rank ? own : qx[(sr < p.rank ? sr : sr - 1) * p.qw + i];
                             acc = (i == rows_c + 1) ? fmax(acc, v) : acc + v;
                         }
@@ -1864,21 +1873,24 @@ extern "C" int b200l_set_tuning(b200l_ctx *c, int32_t slot_bytes_target, int32_t
 
 typedef void (*fused_fn)(const RunParams, const CUtensorMap);
 
-template <typename T>
+template <typename T, bool FULL>
 static fused_fn pick_kernel(int cpt, bool trans) {
-    if (trans) return lasso_fused<T, 1, true>;
+    if (trans) return lasso_fused<T, 1, true, FULL>;
     switch (cpt) {
-        case 1: return lasso_fused<T, 1, false>;
-        case 2: return lasso_fused<T, 2, false>;
-        case 4: return lasso_fused<T, 4, false>;
-        case 8: return lasso_fused<T, 8, false>;
+        case 1: return lasso_fused<T, 1, false, FULL>;
+        case 2: return lasso_fused<T, 2, false, FULL>;
+        case 4: return lasso_fused<T, 4, false, FULL>;
+        case 8: return lasso_fused<T, 8, false, FULL>;
         default: return nullptr;
     }
 }
 
-static fused_fn ctx_kernel(const b200l_ctx *c) {
+// full = multi-GPU, tracing or diagnostic switches in use (see the FULL template parameter)
+static fused_fn ctx_kernel(const b200l_ctx *c, bool full) {
     const bool trans = c->layout == B200L_TRANSPOSED;
-    return c->dtype == B200L_F32 ? pick_kernel<float>(c->cpt, trans) : pick_kernel<double>(c->cpt, trans);
+    if (full)
+        return c->dtype == B200L_F32 ? pick_kernel<float, true>(c->cpt, trans) : pick_kernel<double, true>(c->cpt, trans);
+    return c->dtype == B200L_F32 ? pick_kernel<float, false>(c->cpt, trans) : pick_kernel<double, false>(c->cpt, trans);
 }
 
 // tensor map of the pre-transposed matrix: 2-D (ldT residual entries, nblocks*w columns)
@@ -2043,12 +2055,14 @@ static int plan_geometry(b200l_ctx *c) {
         CK(cudaMemsetAsync(c->gLL, 0, need, c->stream));
     }
 
-    fused_fn fn = ctx_kernel(c);
-    if (!fn) return fail("internal: no kernel for cpt=%d", cpt);
-    CK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_bytes));
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, NTHREADS, c->smem_bytes));
-    if (occ < 1) return fail("fused kernel does not fit on an SM (smem=%d)", c->smem_bytes);
+    for (int full = 0; full < 2; ++full) {
+        fused_fn fn = ctx_kernel(c, full != 0);
+        if (!fn) return fail("internal: no kernel for cpt=%d", cpt);
+        CK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_bytes));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, NTHREADS, c->smem_bytes));
+        if (occ < 1) return fail("fused kernel does not fit on an SM (smem=%d)", c->smem_bytes);
+    }
     int coop = 0;
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
     if (!coop) return fail("device does not support cooperative launch");
@@ -2138,7 +2152,7 @@ static int launch_fused(b200l_ctx *c, const int32_t *order_host, int64_t nsteps,
     p.dbg = c->dbg;
 
     if (c->layout == B200L_TRANSPOSED && !c->tmap_valid && make_tensor_map(c)) return 1;
-    fused_fn fn = ctx_kernel(c);
+    fused_fn fn = ctx_kernel(c, c->world > 1 || trace_dev != nullptr || ttrace_dev != nullptr || (c->dbg & 7) != 0);
     void *args[] = {(void *)&p, (void *)&c->tmap};
     if (timed) CK(cudaEventRecord(c->ev0, c->stream));
     CK(cudaLaunchCooperativeKernel((const void *)fn, dim3(c->grid), dim3(NTHREADS), args,

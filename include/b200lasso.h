@@ -131,7 +131,8 @@ int b200l_set_tuning(b200l_ctx *ctx, int32_t slot_bytes_target, int32_t max_infl
  * B200L_NTRACE time stamps in ns since kernel start: [0] step start, [1] pass 1 (A_m^T r)
  * done, [2] partial gradient published, [3] my columns gathered, [4] partials combined,
  * [5] pending step resolved (gamma), [6] prox done / D published, [7] D gathered,
- * [8] pass 2 (A_m D) done, [9] line-search partials done.  trace_host holds
+ * [8] pass 2 (A_m D) done, [9] line-search partials done, [10] first inbox fetch landed,
+ * [11] number of inbox fetches of the step.  trace_host holds
  * grid*nsteps*B200L_NTRACE uint64 (grid = b200l_run_config's grid, also returned in grid_out).
  * No counterpart in the reference (its only timer is lasso.py:234-236). */
 int b200l_run_traced(b200l_ctx *ctx, int64_t nsteps, double mu, uint64_t *trace_host,
