@@ -189,16 +189,18 @@ def run_cpu(orc, A, b, mu, BLOCK, sweeps):
     return o["elapsed"]
 
 
-def cpu_baseline_block(sweeps=6):
+def cpu_baseline_block(seconds=12.0):
+    """about `seconds` of CPU work: as many sweeps of the sample as fit (oracle time_limit)"""
     orc, A, b, mu, N, K, BLOCK = cpu_sample()
     run_cpu(orc, A, b, mu, BLOCK, 1)
-    dt = run_cpu(orc, A, b, mu, BLOCK, sweeps)
+    o = orc.lasso_oracle(A, b, mu, BLOCK, BLOCK * 100000, None, faithful=False, time_limit=seconds)
+    sweeps, dt = o["iters"] / float(BLOCK), o["elapsed"]
     frac = K / C2["K"]
     sample_sweeps_per_s = sweeps / dt
     return {"value": sample_sweeps_per_s * frac, "unit": UNIT, "cores": os.cpu_count(),
             "kind": "port",
             "sample": "oracle port (NumPy fp64, BLAS threads) on 10000x10000, 10 blocks of w=1000 "
-                      "(1/10 of the C2 columns), %d sweeps in %.2f s = %.2f sample-sweeps/s; value is "
+                      "(1/10 of the C2 columns), %.1f sweeps in %.2f s = %.2f sample-sweeps/s; value is "
                       "scaled by bytes (x%.2f) to the full 10000x100000 sweep" % (sweeps, dt, sample_sweeps_per_s, frac)}
 
 
