@@ -54,12 +54,13 @@ def measured_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(layout):
-    """dram bytes per sweep from the committed ncu --set full capture, if any"""
+def ncu_traffic(config, layout):
+    """dram bytes per sweep from the committed ncu --set full capture of this workload, if any"""
     path = os.path.join(ROOT, "profiles", "traffic.json")
+    key = layout if config == "c2" else "%s_%s" % (config, layout)
     try:
         with open(path) as f:
-            return json.load(f).get(layout)
+            return json.load(f).get(key)
     except Exception:
         return None
 
@@ -360,7 +361,7 @@ def main_gpu(args):
         W = sweep_bytes(N, K, BLOCK, s)
         peak, peak_src = measured_peak()
         achieved = W / (kernel_ms * 1e-3) / 1e9
-        traffic = ncu_traffic(layout)
+        traffic = None if args.small else ncu_traffic(args.config, layout)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,

@@ -19,7 +19,7 @@ INCLUDE = os.path.join(_ROOT, "include")
 HEADER = os.path.join(INCLUDE, "b200lasso.h")
 
 F32, F64 = 0, 1
-NTRACE = 12
+NTRACE = 16
 NTTRACE = 96
 IPC_HANDLE_BYTES = 64
 ROWMAJOR, TRANSPOSED = 0, 1
