@@ -335,6 +335,7 @@ def main_gpu(args):
     kernel_ms_alone = float(np.mean(ktimes))
     obj = ctypes.c_double()
     _lib.check(lib.b200l_objective(ctx, float(mu), ctypes.byref(obj)))
+    obj_bench = obj.value
 
     # ---- e2e: through ClassLasso.run(), host b in, host x out -------------------------
     e2e_sweeps = args.e2e_sweeps
@@ -357,6 +358,18 @@ def main_gpu(args):
     e2e_value = world * e2e_steps * e2e_sweeps / e2e_dt
     nnz = int(np.count_nonzero(solver.x))
 
+    # ---- time-to-eps: cold start (x = 0) to the reference's stop rule (lasso.py:141-150) ----
+    tte = None
+    if args.eps > 0:
+        _lib.check(lib.b200l_reset(ctx))
+        steps_done, stopped = ctypes.c_int64(), ctypes.c_int32()
+        _lib.check(lib.b200l_run(ctx, None, BLOCK * args.eps_max_sweeps, float(mu), float(args.eps), None, None,
+                                 ctypes.byref(steps_done), ctypes.byref(stopped), ctypes.byref(kms)))
+        _lib.check(lib.b200l_objective(ctx, float(mu), ctypes.byref(obj)))
+        tte = {"eps": args.eps, "ms": kms.value, "sweeps": steps_done.value / BLOCK,
+               "reached": bool(stopped.value), "objective": obj.value,
+               "note": "device time of one launch from x = 0 until every block of a sweep has error_crit < eps"}
+
     if rank == 0:
         W = sweep_bytes(N, K, BLOCK, s)
         peak, peak_src = measured_peak()
@@ -375,7 +388,7 @@ def main_gpu(args):
                                        "A_m D summed in-kernel over NVLink peer memory); value counts C2-sized "
                                        "shard sweeps: %d per sweep of the %dx%d instance"
                                        % (world, world, N, K * world)) if world > 1 else ""),
-                       "launch": geo, "objective_after_bench": obj.value},
+                       "launch": geo, "objective_after_bench": obj_bench},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "kernel": "lasso_fused<%s,1,%s>" % ("float" if s == 4 else "double",
@@ -395,6 +408,8 @@ def main_gpu(args):
             "gpu_launches": args.steps,
             "clocks": clocks,
         }
+        if tte:
+            line["time_to_eps"] = tte
         if not args.no_cpu and world == 1:
             line["cpu_baseline"] = cpu_baseline_block()
         print(json.dumps(line))
@@ -414,6 +429,8 @@ def main():
     ap.add_argument("--small", action="store_true", help="2000x20000 debug size (not a bench value)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-sweeps", type=int, default=5)
+    ap.add_argument("--eps", type=float, default=1e-4, help="ERR_BOUND of the time-to-eps leg (0 = skip)")
+    ap.add_argument("--eps-max-sweeps", type=int, default=2000)
     ap.add_argument("--slot-bytes", type=int, default=0)
     ap.add_argument("--inflight", type=int, default=0)
     ap.add_argument("--dbg", type=int, default=0, help="diagnostic flags of b200l_debug_flags (not for bench values)")

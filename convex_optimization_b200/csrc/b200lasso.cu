@@ -275,8 +275,8 @@ template <> struct LLW<double> {
 
 constexpr int NTTRACE = 96;        // per-tile stamps: 6 groups of 16 (see b200lasso.h)
 constexpr int NTRACE = 16;         // time stamps per CTA and step of b200l_run_traced
-constexpr int PPL = 5;             // source CTAs per lane in the gather: grid <= 32 * PPL
-constexpr int GMAX = 32 * PPL;     // = 160
+constexpr int NLD = 10;            // source CTAs per lane in the gather: grid <= 16 * NLD
+constexpr int GMAX = 16 * NLD;     // = 160
 
 // ------------------------------------------------------------------------------------
 // fused kernel parameters
@@ -839,7 +839,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                         LL::put(out + (size_t)rd * G * MW + 4 + jj * WPC, (T)0, (T)0, tag);
                     }
                 }
-                const int npad = MW - 4 - cs * WPC;                     // 0..2 padding words
+                const int npad = MW - 4 - cs * WPC;                     // 1..4 padding words
 #pragma unroll 1
                 for (int e2 = tid; e2 < G * 8; e2 += NTC) {
                     const int rd = e2 >> 3, k = e2 & 7;
@@ -892,71 +892,63 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                         }
                         if (cbar_or(*(volatile int *)&ctl->abort != 0)) break;
                     }
-                    // two virtual columns per warp and trip.  Straight-line on purpose: the loads are
-                    // unconditional (clamped source index) and issued as one batch, lanes past the
-                    // last source are masked by selects -- a branch per load serialises the
-                    // shared-memory latencies (measured: 1.4 us instead of 0.3 us per step)
+                    // column sums: warp = a pair of adjacent message words (2pr, 2pr+1), lane =
+                    // (source lane/2 + 16i, word lane%2).  The message length is 2 (mod 4) words, so
+                    // the 8 lanes of a quarter warp hit 8 different 16-byte bank groups.  Straight-line
+                    // on purpose: the loads go out as one batch (a branch per load serialises the
+                    // shared-memory latencies: measured 1.4 us instead of 0.3 us per step); lanes
+                    // past the last source read a padding word, which decodes to zero.
+                    {
+                        const int sub = lane & 1, srcl = lane >> 1;
+                        const int nwd = 4 + cs * WPC;
+                        double *csd = reinterpret_cast<double *>(colsum);
 #pragma unroll 1
-                    for (int vc0 = wid; vc0 < nvc; vc0 += 2 * NW) {
-                        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-                        ulonglong2 w0[2][PPL], w1[2][PPL];
+                        for (int pr = wid; 2 * pr < nwd; pr += NW) {
+                            const int word = 2 * pr + sub;
+                            ulonglong2 w[NLD];
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int vc = min(vc0 + h * NW, nvc - 1);
-                            const int wi = vc < 4 ? vc : 4 + (vc - 4) * WPC;
-#pragma unroll
-                            for (int i = 0; i < PPL; ++i) {
-                                const int pp = min(lane + 32 * i, gn - 1);
-                                w0[h][i] = stage[pp * MW + wi];
-                                if (WPC == 2) w1[h][i] = stage[pp * MW + min(wi + 1, MW - 1)];
+                            for (int i = 0; i < NLD; ++i) {
+                                const int src = srcl + 16 * i;
+                                w[i] = stage[src < gn ? src * MW + word : MW - 1];
                             }
-                        }
+                            const bool dbl = WPC == 2 || pr < 2;     // fp64 words (warp-uniform)
+                            const bool has_max = dbl && pr == 1;     // word 3 is a maximum
+                            double a0 = 0.0, a1 = 0.0;
+                            if (dbl) {
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int vc = vc0 + h * NW;
-                            const bool is_s = vc < 4, is_max = vc == 3;
+                                for (int i = 0; i < NLD; ++i) a0 += ll_dbl(w[i]);
+                                if (has_max) {
 #pragma unroll
-                            for (int i = 0; i < PPL; ++i) {
-                                const bool valid = lane + 32 * i < gn;
-                                double va, vb;
-                                if (WPC == 1) {
-                                    const double vs = ll_dbl(w0[h][i]);
-                                    const double vr = (double)__uint_as_float((uint32_t)w0[h][i].x);
-                                    const double vq = (double)__uint_as_float((uint32_t)w0[h][i].y);
-                                    va = is_s ? vs : vr;
-                                    vb = is_s ? 0.0 : vq;
-                                } else {
-                                    va = ll_dbl(w0[h][i]);
-                                    vb = is_s ? 0.0 : ll_dbl(w1[h][i]);
+                                    for (int i = 0; i < NLD; ++i) a1 = fmax(a1, ll_dbl(w[i]));
                                 }
-                                va = valid ? va : 0.0;          // scalars and partial sums: 0 is neutral
-                                vb = valid ? vb : 0.0;          // (the error terms are >= 0)
-                                acc[h][0] = is_max ? fmax(acc[h][0], va) : acc[h][0] + va;
-                                acc[h][1] += vb;
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < NLD; ++i) {
+                                    a0 += (double)__uint_as_float((uint32_t)w[i].x);
+                                    a1 += (double)__uint_as_float((uint32_t)w[i].y);
+                                }
                             }
-                        }
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                const double oa = __shfl_xor_sync(0xffffffffu, acc[h][0], o);
-                                const double ob = __shfl_xor_sync(0xffffffffu, acc[h][1], o);
-                                acc[h][0] = (vc0 + h * NW == 3) ? fmax(acc[h][0], oa) : acc[h][0] + oa;
-                                acc[h][1] += ob;
+                            for (int o = 2; o < 32; o <<= 1) {
+                                const double oa = __shfl_xor_sync(0xffffffffu, a0, o);
+                                const double ob = __shfl_xor_sync(0xffffffffu, a1, o);
+                                a0 += oa;
+                                a1 = has_max ? fmax(a1, ob) : a1 + ob;
                             }
-                        }
-                        if (lane == 0) {
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                const int vc = vc0 + h * NW;
-                                if (vc < nvc) {
-                                    double a = acc[h][0], bq = acc[h][1];
+                            if (lane < 2 && word < nwd) {
+                                if (dbl) {
+                                    // scalar k -> colsum[k].x; fp64 column j -> colsum[4 + j].(x | y)
+                                    const int at = word < 4 ? 2 * word : 2 * (4 + ((word - 4) >> 1)) + sub;
+                                    double v = word == 3 ? a1 : a0;
+                                    if (g0 > 0) v = word == 3 ? fmax(v, csd[at]) : v + csd[at];
+                                    csd[at] = v;
+                                } else {
                                     if (g0 > 0) {
-                                        const double2 o = colsum[vc];
-                                        a = vc == 3 ? fmax(a, o.x) : a + o.x;
-                                        bq += o.y;
+                                        const double2 o = colsum[word];
+                                        a0 += o.x;
+                                        a1 += o.y;
                                     }
-                                    colsum[vc] = make_double2(a, bq);
+                                    colsum[word] = make_double2(a0, a1);
                                 }
                             }
                         }
@@ -2035,17 +2027,16 @@ static int plan_geometry(b200l_ctx *c) {
     c->grid = G;
     c->cpt = cpt;
     c->nt_max = nt_max;
-    // exchange geometry: message = 4 scalars + cs columns, padded to an odd word count (bank
-    // spread of the per-source reads); both exchange fetches land in one ring slot
+    // exchange geometry; both exchange fetches land in one ring slot
     const int wpc = es / 4;
-    // publishing from registers needs complete column sums per thread (one row group), a
-    // column group inside one message and 32-byte aligned messages (even word count)
+    // publishing from registers needs complete column sums per thread (one row group) and a
+    // column group inside one message
     const int direct = trans ? 1 : ((nrg == 1 && cs * wpc >= 4 && !(c->dbg & 128)) ? 1 : 0);
-    int mw = (4 + cs * wpc) | 1;
-    if (direct && !trans) {                      // 32-byte aligned messages: even, with an odd half
-        mw = (4 + cs * wpc + 1) & ~1;
-        if ((mw / 2) % 2 == 0) mw += 2;
-    }
+    // message = 4 scalars + cs columns + 1..4 padding words, 2 (mod 4) words long: even for the
+    // 256-bit stores of the register publish, and with an odd half so that the pair-wise reads
+    // of the gather are free of bank conflicts
+    int mw = 4 + cs * wpc + 1;
+    while (mw % 4 != 2) ++mw;
     const int slot_words = slot_bytes / 16;
     int gc = G;
     if (G * mw > slot_words) {

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--block", type=int, default=C2["BLOCK"])
     ap.add_argument("--dtype", default="float")
     ap.add_argument("--sweeps", type=int, default=3)
+    ap.add_argument("--layout", default="row", choices=["row", "transposed"])
     ap.add_argument("--slot-bytes", type=int, default=0)
     ap.add_argument("--inflight", type=int, default=0)
     ap.add_argument("--sweep", default="", help="semicolon list of slot,inflight[,dbg] tuples")
@@ -37,10 +38,11 @@ def main():
 
     class Cal(GPU_Calculation):
         TYPE = args.dtype
+        LAYOUT = args.layout
     dev = torch.device("cuda", 0)
     tdt = torch.float32 if args.dtype == "float" else torch.float64
     ld = Cal.padded_ld(N, K, BLOCK)
-    store, b, mu = make_device_instance(torch, dev, N, K, BLOCK, 0.01, 2, tdt, ld)
+    store, b, mu = make_device_instance(torch, dev, N, K, BLOCK, 0.01, 2, tdt, ld, args.layout)
     cal = Cal.from_device_blocks(store, N, K, BLOCK)
     lib, ctx = cal._lib, cal.ctx
     bb = np.ascontiguousarray(b.reshape(-1))
@@ -88,12 +90,21 @@ def main():
                "phases_us_min_cta": {n: round(float(dur[:, :, i].mean(axis=1).min()), 3) for i, n in enumerate(PHASES)},
                "skew_us_pass1_end": float((s[:, :, 1].max(axis=0) - s[:, :, 1].min(axis=0)).mean()),
                "skew_us_step_start": float((s[:, :, 0].max(axis=0) - s[:, :, 0].min(axis=0)).mean())}
+        if NT >= 15:        # inside "gather g": fetch landed, tags checked, barrier, column sums (last fetch)
+            f = tr.astype(np.float64)[:, BLOCK:, :] * 1e-3
+            out["gather_g_detail_us"] = {
+                "publish end -> first fetch landed": round(float((f[:, :, 10] - f[:, :, 2]).mean()), 3),
+                "fetch landed -> tags checked (incl. refetches)": round(float((f[:, :, 12] - f[:, :, 10]).mean()), 3),
+                "barrier": round(float((f[:, :, 13] - f[:, :, 12]).mean()), 3),
+                "column sums": round(float((f[:, :, 14] - f[:, :, 13]).mean()), 3),
+                "closing barrier": round(float((f[:, :, 3] - f[:, :, 14]).mean()), 3),
+                "fetches per step": round(float(tr[:, BLOCK:, 11].mean()), 3)}
         results.append(out)
         if args.raw:
             np.save("%s_%d_%d_%d.npy" % (args.raw, slot, infl, dbg), tr)
             np.save("%s_tiles_%d_%d_%d.npy" % (args.raw, slot, infl, dbg), tt[::16])
         print(json.dumps({k: out[k] for k in ("tuning", "ms_per_sweep", "sweeps_per_s", "us_per_block_step",
-                                               "phases_us_mean_over_ctas", "skew_us_pass1_end")}))
+                                               "phases_us_mean_over_ctas", "skew_us_pass1_end", "gather_g_detail_us") if k in out}))
         sys.stdout.flush()
     out = results if len(results) > 1 else results[0]
     if args.out:
