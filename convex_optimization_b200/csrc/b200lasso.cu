@@ -60,6 +60,7 @@ static int fail(const char *fmt, ...) {
 constexpr int NW = 8;                  // consumer warps
 constexpr int NTC = NW * 32;           // consumer threads
 constexpr int NTHREADS = NTC + 32;     // + one producer warp
+constexpr int NTHREADS_MG = NTC + 64;  // multi-GPU: + one warp that collects the peers' rows
 constexpr int MAX_CS = 64;             // max stage-2 slice width (columns per CTA)
 
 template <typename T> struct VT;
@@ -287,6 +288,10 @@ struct Ctl {
     int stop;
     int abort;
     long long gate;                  // steps whose pass-2 copies the producer may issue
+    long long qready;                // multi-GPU: (step + 1) << 32 | rows of A_m D summed over the ranks
+    long long p2start, p2done;       // multi-GPU: steps whose pass 2 (my partial rows) has begun / is complete
+    int hstop;                       // multi-GPU: the consumers are done, the collector warp exits
+    unsigned long long t_start;      // time base of the phase trace
 };
 
 struct RunParams {
@@ -319,7 +324,7 @@ struct RunParams {
     // multi-GPU: rank `rank` of `world` holds column slice `rank` of every block; peer[r] is the
     // q-inbox of rank r: [2 parities][G CTAs][world sources][qw] words (peer[rank] is local)
     int32_t xmode;            // cross-rank exchange: 0 per-tile sends + bulk-copy gather, 1 per-row sends + polled gather
-    int32_t world, rank, qw, qx_words;   // qx_words: the cell of a step fits the landing area
+    int32_t world, rank, qw, qx_words;   // qx_words != 0: the collector warp sends the partial rows tile by tile
     ulonglong2 *peer[B200L_MAX_WORLD];
     int32_t direct_pub;       // partial gradients are published from registers (one row group)
     int32_t gate_mode;        // 0: re-stream freely, 1/2/3: after inbox fetch issued / gather done / D fetch issued
@@ -465,7 +470,7 @@ __device__ __forceinline__ T warp_sum_pair(const T a, const T b, const int lane)
 //       plain single-GPU solve runs the FULL = false instantiation: the per-step code has to
 //       stay resident in the instruction cache and every rarely used branch costs footprint.
 template <typename T, int CPT, bool TRANS, bool FULL>
-__global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(const RunParams p, const __grid_constant__ CUtensorMap tmap) {
     using VecT = typename VT<T>::type;
     using LL = LLW<T>;
     using OP = Ops<T>;
@@ -509,7 +514,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
     const T *Aall = reinterpret_cast<const T *>(p.A);
 
     // the ring starts zero-filled (defined contents for the parts of a slot no copy writes)
-    for (int i = tid; i < p.ring_bytes / 16; i += NTHREADS)
+    for (int i = tid; i < p.ring_bytes / 16; i += (int)blockDim.x)
         reinterpret_cast<uint4 *>(ring)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
@@ -521,6 +526,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
         ctl->stop = 0;
         ctl->abort = 0;
         ctl->gate = 0;
+        ctl->qready = 0;
+        ctl->p2done = 0;
+        ctl->p2start = 0;
+        ctl->hstop = 0;
         for (int i = 0; i < 128; ++i) tilecnt[i] = 0;
         ctl->kc = 0;
         ctl->k_issued = 0;
@@ -604,7 +613,153 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
             ctl->k_issued = k;
         }
         __syncwarp();
-    } else {
+    } else if (wid == NW + 1) {
+        // ============== multi-GPU: collector of the peers' partial A_m D ===========
+        // (the reduce of lasso.py:126 over the reference's P column slices).  CTA c of every
+        // rank owns the same rows; during pass 2 each rank stores its finished rows (and its
+        // l1 / err terms) as tagged words straight into the inbox of CTA c on every peer
+        // (NVLink peer stores).  This warp collects them while the consumers already run
+        // pass 1 of the next step -- which needs the summed rows tile by tile, in the order
+        // they were sent -- so the NVLink latency hides behind the streaming.  Sums in rank
+        // order: every rank holds bitwise the same q, gamma and r.  Cells are double-buffered
+        // by step parity: a rank can be at most one exchange ahead.
+        if (WORLD > 1) {
+            Waiter hw{p.abort_flag, &ctl->abort, p.wait_limit_ns, 0u, 0ull, p.state + 4, 0};
+            const int nq = rows_c + 2;                       // rows, then the l1 and err terms
+            bool live = true;
+            for (long long hs = 0; live; ++hs) {
+                const uint32_t tag = p.tag_base + (uint32_t)hs + 1u;
+                const ulonglong2 *mycell = p.peer[p.rank] + (((size_t)(tag & 1u) * G + c) * WORLD) * p.qw;
+                double trq = 0.0, tqq = 0.0;
+                bool own_ready = false;                      // my own pass 2 of step hs is complete
+                unsigned spin = 0;
+                // nothing can arrive before the ranks are in pass 2 of this step: nap until mine
+                // begins (shared-memory flag, no L2 traffic)
+                while (!__all_sync(0xffffffffu, *(volatile long long *)&ctl->p2start > hs)) {
+                    if (__any_sync(0xffffffffu, *(volatile int *)&ctl->hstop != 0)) {
+                        live = false;
+                        break;
+                    }
+                    __nanosleep(64);
+                }
+                if (!live) break;
+                hw.begin((hs << 32) | (2LL << 30));
+                if (p.xmode == 0) {
+                    // my partial rows go to the peers tile by tile, as soon as the 8 consumer warps are
+                    // done with a tile: consecutive lanes = consecutive words (whole NVLink packets),
+                    // and the stores stay out of the inner loop of pass 2
+                    const size_t mine = (((size_t)(tag & 1u) * G + c) * WORLD + p.rank) * p.qw;
+#pragma unroll 1
+                    for (int t = 0; t < nt; ++t) {
+                        while (!__all_sync(0xffffffffu, *(volatile int *)&tilecnt[t & 127] >= NW)) {
+                            if (!__all_sync(0xffffffffu, hw.again())) break;
+                        }
+                        __threadfence_block();
+                        const int rows_t = min(TR, rows_c - t * TR);
+#pragma unroll 1
+                        for (int i = lane; i < rows_t; i += 32) {
+                            const double v = qpart[t * TR + i];
+#pragma unroll 1
+                            for (int pr = 0; pr < WORLD; ++pr)
+                                if (pr != p.rank) ll_st_dbl(p.peer[pr] + mine + t * TR + i, v, tag);
+                        }
+                        __syncwarp();
+                        if (lane == 0) tilecnt[t & 127] = 0;
+                        if (DBG & 1024) __threadfence_system();
+                    }
+                    own_ready = true;
+                    __threadfence_block();
+                }
+#pragma unroll 1
+                for (int i0 = 0; i0 < nq && live; i0 += 64) {        // 2 x 32 words x (world-1) sources in flight
+                    ulonglong2 w[2][B200L_MAX_WORLD - 1];
+                    bool done[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int i = i0 + 32 * h + lane;
+                        done[h] = i >= nq;
+#pragma unroll
+                        for (int k = 0; k < B200L_MAX_WORLD - 1; ++k)
+                            if (k < WORLD - 1)
+                                w[h][k] = ll_ld(mycell + (size_t)(k < p.rank ? k : k + 1) * p.qw + min(i, nq - 1));
+                    }
+                    // the peers' words are polled from the moment the previous step is finished; a
+                    // row is summed (rank order) and released to pass 1 as soon as it is complete
+                    // and every row before it is
+                    for (;;) {
+                        if (!own_ready) {
+                            own_ready = __all_sync(0xffffffffu, *(volatile long long *)&ctl->p2done > hs);
+                            if (own_ready) {
+                                __threadfence_block();
+                            } else if (__any_sync(0xffffffffu, *(volatile int *)&ctl->hstop != 0)) {
+                                live = false;                // the consumers are gone: no step hs
+                                break;
+                            }
+                        }
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            if (!done[h]) {
+                                const int i = i0 + 32 * h + lane;
+                                bool ok = true;
+#pragma unroll
+                                for (int k = 0; k < B200L_MAX_WORLD - 1; ++k) {
+                                    if (k < WORLD - 1 && !ll_ok(w[h][k], tag)) {
+                                        ok = false;
+                                        w[h][k] = ll_ld(mycell + (size_t)(k < p.rank ? k : k + 1) * p.qw + i);
+                                    }
+                                }
+                                if (ok && own_ready) {
+                                    const double own = i < rows_c ? qpart[i] : ctl->sp[2 + (i - rows_c)];
+                                    const bool is_max = i == rows_c + 1;
+                                    double acc = 0.0;
+#pragma unroll
+                                    for (int k = 0; k < B200L_MAX_WORLD; ++k) {
+                                        if (k == p.rank) acc = is_max ? fmax(acc, own) : acc + own;
+                                        if (k < B200L_MAX_WORLD - 1 && k < WORLD - 1) {
+                                            const double v = ll_dbl(w[h][k]);
+                                            acc = is_max ? fmax(acc, v) : acc + v;
+                                        }
+                                    }
+                                    if (i < rows_c) {
+                                        q_loc[i] = acc;
+                                        qT[i] = (T)acc;
+                                        trq += r_loc[i] * acc;                           // lasso.py:129
+                                        tqq += acc * acc;                                // lasso.py:132
+                                    } else {
+                                        ctl->sp[2 + (i - rows_c)] = acc;
+                                    }
+                                    done[h] = true;
+                                }
+                            }
+                        }
+                        // watchdog every 16th trip (the poll period is the L2 round trip)
+                        if (((++spin & 15u) == 0u && !__all_sync(0xffffffffu, hw.again())) || (DBG & 1)) {
+                            done[0] = done[1] = true;        // aborted: the consumers find the abort flag
+                        }
+                        const unsigned nd0 = __ballot_sync(0xffffffffu, !done[0]);
+                        const unsigned nd1 = __ballot_sync(0xffffffffu, !done[1]);
+                        const int ready = nd0 ? i0 + __ffs(nd0) - 1 : (nd1 ? i0 + 32 + __ffs(nd1) - 1 : i0 + 64);
+                        __threadfence_block();
+                        if (lane == 0)
+                            *(volatile long long *)&ctl->qready = ((hs + 1) << 32) | (long long)min(ready, rows_c);
+                        if (!(nd0 | nd1)) break;
+                    }
+                }
+                if (!live) break;
+                trq = warp_sum(trq);
+                tqq = warp_sum(tqq);
+                if (lane == 0) {
+                    ctl->sp[0] = trq;
+                    ctl->sp[1] = tqq;
+                    __threadfence_block();
+                    *(volatile long long *)&ctl->qready = ((hs + 1) << 32) | 0x7fffffffLL;
+                    if (p.trace)
+                        p.trace[((size_t)c * p.nsteps + hs) * NTRACE + 15] =
+                            globaltimer_ns() - *(volatile unsigned long long *)&ctl->t_start;
+                }
+            }
+        }
+    } else if (wid < NW) {
         // ============================ consumer warps ===============================
         for (int i = tid; i < rows_c; i += NTC) {
             const double rv = p.r[row0 + i];
@@ -631,11 +786,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
         int stopped = 0, aborted = 0;
         int64_t steps_done = 0;
         const unsigned long long t_start = globaltimer_ns();
+        if (FULL && tid == 0) ctl->t_start = t_start;
         const int cs = p.cs, nrg = p.nrg;
         const double mu = p.mu;
         const uint32_t tag0 = p.tag_base;
         const ulonglong2 *inbox = p.gLL + (size_t)c * G * p.mw;
         Waiter waiter{p.abort_flag, &ctl->abort, p.wait_limit_ns, 0u, 0ull, p.state + 4, 0};
+        // multi-GPU: wait until the collector warp has summed `rows` rows of the pending step's
+        // A_m D over the ranks (0x7fffffff: all rows and the scalars)
+        auto wait_q = [&](int64_t pending_step, int rows) {
+            const long long want = ((pending_step + 1) << 32) | (long long)rows;
+            while (*(volatile long long *)&ctl->qready < want) {
+                if (*(volatile int *)&ctl->abort) break;
+            }
+            __threadfence_block();
+        };
         unsigned long long *trace =
             (FULL && p.trace != nullptr && tid == 0) ? p.trace + (size_t)c * p.nsteps * NTRACE : nullptr;
         unsigned long long *ttrace =
@@ -698,6 +863,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                     const T *tile = reinterpret_cast<const T *>(ring + (size_t)cur.slot * p.slot_bytes);
                     const int rows_t = min(TR, rows_c - t * TR);
                     const T *rTt = rT + t * TR, *qTt = qT + t * TR;
+                    if (WORLD > 1 && have_prev) wait_q(step_prev, TRANS ? rows_c : t * TR + rows_t);
                     if (TRANS) {
                         // thread = block column t*TJ + tid: dot products of its BX entries with r and q,
                         // complete for this CTA's rows, published at once (one tagged word per column)
@@ -807,6 +973,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                     }
                 }
             }
+            if (WORLD > 1 && have_prev) wait_q(step_prev, 0x7fffffff);
             cbar();
             // ---------------- publish: one message of MW words per reader -------------------
             // [0..3] my line-search scalars of the pending step, [4..] the partial gradient of
@@ -1104,10 +1271,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
             if (tid == 0) {                // my l1 / err terms of this step travel with the rows
                 send_row(rows_c, ctl->sp[2]);
                 send_row(rows_c + 1, ctl->sp[3]);
+                if (WORLD > 1) *(volatile long long *)&ctl->p2start = step + 1;
             }
 
             // ---------------- pass 2: q = A_m D over the slab ---------------------------
-            int hold2 = -1;                // multi-GPU: ring slot of the last pass-2 tile, held for the exchange
             Acc accT;                      // TRANS: this thread's residual entries, all columns
             OP::zero(accT);
             const int ivT = TRANS ? tid % p.BXV : 0, partT = TRANS ? tid / p.BXV : 0;
@@ -1180,30 +1347,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                             }
                         }
                         if (WORLD > 1 && p.xmode == 0) {
-                            // multi-GPU: the warp that completes a tile sends its rows to every peer,
-                            // consecutive lanes = consecutive words (whole NVLink packets), while the
-                            // other warps go on with the next tile
+                            // multi-GPU: count the warps that are done with this tile; the collector
+                            // warp sends the tile's rows to the peers when all are
                             __syncwarp();
-                            int last = 0;
-                            if (nt > 128) {            // more tiles than counters: every warp sends its own rows
-                                if (lane == 0)
-                                    for (int r2 = wid; r2 < rows_t; r2 += NW) send_row(t * TR + r2, qpart[t * TR + r2]);
-                            } else if (lane == 0) {
+                            if (lane == 0) {
                                 __threadfence_block();
-                                last = atomicAdd(tilecnt + (t2 & 127), 1) == NW - 1;
-                            }
-                            last = __shfl_sync(0xffffffffu, last, 0);
-                            if (last) {
-                                __threadfence_block();
-#pragma unroll 1
-                                for (int i = lane; i < rows_t; i += 32) send_row(t * TR + i, qpart[t * TR + i]);
-                                if (lane == 0) tilecnt[t2 & 127] = 0;
+                                atomicAdd(tilecnt + (t2 & 127), 1);
                             }
                         }
                     }
                     __syncwarp();
-                    if (FULL && p.qx_words && t2 == nt - 1) hold2 = slot;      // landing area of the rank exchange
-                    else if (lane == 0) mbar_arrive(empty + slot);
+                    if (lane == 0) mbar_arrive(empty + slot);
                     if (ttrace && t2 < 16) ttrace[step * NTTRACE + 48 + t2] = globaltimer_ns();
                 }
             }
@@ -1225,90 +1379,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
             }
             if (trace) trace[step * NTRACE + 8] = globaltimer_ns() - t_start;
             if (WORLD > 1) {
-                // ---------------- multi-GPU: sum the partial A_m D over the ranks ----------
-                // (the reduce of lasso.py:126 over the reference's P column slices).  CTA c of
-                // every rank owns the same rows; during pass 2 it stored its rows_c partial sums
-                // and its l1 / err terms as tagged words straight into the inbox of CTA c on every
-                // peer (NVLink peer stores).  Here it collects the world-1 contributions (threads
-                // = (word, source) pairs, through shared memory) and adds them up in rank order,
-                // so every rank holds bitwise the same q and the replicated r stays identical.
-                // Double-buffered by step parity: a rank can be at most one exchange ahead.
-                const int nq = rows_c + 2;
-                const ulonglong2 *mycell = p.peer[p.rank] + cell;              // [world][qw] words
-                if (p.qx_words) {
-                    // the whole cell (all sources, contiguous) comes in by one bulk copy; threads
-                    // check the tags, poll a missing word in L2, and the copy is repeated
-                    // ... into the ring slot of the last pass-2 tile (slot 0 when this CTA has no rows)
-                    ulonglong2 *qxw = reinterpret_cast<ulonglong2 *>(ring + (size_t)(hold2 >= 0 ? hold2 : 0) * p.slot_bytes);
-                    const int nwords = WORLD * p.qw;
-                    for (;;) {
-                        if (tid == 0) {
-                            mbar_expect_tx(xbar, (uint32_t)nwords * 16u);
-                            tma_bulk_g2s(qxw, mycell, (uint32_t)nwords * 16u, xbar);
-                        }
-                        mbar_wait(xbar, xphase);
-                        xphase ^= 1u;
-                        int bad = -1;
-#pragma unroll 1
-                        for (int e = tid; e < nq * WORLD; e += NTC) {
-                            const int sr = e / nq, i = e - sr * nq;
-                            if (sr != p.rank && !ll_ok(qxw[sr * p.qw + i], tag)) bad = sr * p.qw + i;
-                        }
-                        if (!cbar_or(bad >= 0) || (DBG & 1)) break;
-                        if (bad >= 0) {
-                            waiter.begin(((long long)step << 32) | (1LL << 30) | (long long)bad);
-                            while (!ll_ok(ll_ld(mycell + bad), tag)) {
-                                if (!waiter.again()) break;
-                            }
-                        }
-                        if (cbar_or(*(volatile int *)&ctl->abort != 0)) break;
-                    }
-#pragma unroll 1
-                    for (int i = tid; i < nq; i += NTC) {
-                        const double own = i < rows_c ? qpart[i] : ctl->sp[2 + (i - rows_c)];
-                        double acc = 0.0;
-#pragma unroll 1
-                        for (int sr = 0; sr < WORLD; ++sr) {
-                            const double v = sr == p.rank ? own : ll_dbl(qxw[sr * p.qw + i]);
-                            acc = (i == rows_c + 1) ? fmax(acc, v) : acc + v;
-                        }
-                        if (i < rows_c) qpart[i] = acc;
-                        else ctl->sp[2 + (i - rows_c)] = acc;
-                    }
-                    if (hold2 >= 0) {              // the landing area goes back to the producer
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(empty + hold2);
-                    }
-                } else {
-                    double *qx = reinterpret_cast<double *>(smem + p.off_qx);  // [world-1][qw]
-#pragma unroll 1
-                    for (int e = tid; e < nq * (WORLD - 1); e += NTC) {
-                        const int k = e / nq, i = e - k * nq;
-                        const int sr = k < p.rank ? k : k + 1;
-                        const ulonglong2 *wp = mycell + (size_t)sr * p.qw + i;
-                        ulonglong2 w = ll_ld(wp);
-                        waiter.begin(((long long)step << 32) | (1LL << 30) | (long long)(sr * 65536 + i));
-                        while (!ll_ok(w, tag) && !(DBG & 1)) {
-                            if (!waiter.again()) break;
-                            w = ll_ld(wp);
-                        }
-                        qx[k * p.qw + i] = ll_dbl(w);
-                    }
-                    cbar();
-#pragma unroll 1
-                    for (int i = tid; i < nq; i += NTC) {
-                        const double own = i < rows_c ? qpart[i] : ctl->sp[2 + (i - rows_c)];
-                        double acc = 0.0;
-#pragma unroll 1
-                        for (int sr = 0; sr < WORLD; ++sr) {
-                            const double v = sr == p.rank ? own : qx[(sr < p.rank ? sr : sr - 1) * p.qw + i];
-                            acc = (i == rows_c + 1) ? fmax(acc, v) : acc + v;
-                        }
-                        if (i < rows_c) qpart[i] = acc;
-                        else ctl->sp[2 + (i - rows_c)] = acc;
-                    }
+                // multi-GPU: my partial rows are complete (and sent); the collector warp sums them
+                // with the peers' rows and computes the line-search partials while the next step's
+                // pass 1 is already running (see the collector warp above)
+                if (tid == 0) {
+                    __threadfence_block();
+                    *(volatile long long *)&ctl->p2done = step + 1;
                 }
-            }
+            } else
             {
                 double trq = 0.0, tqq = 0.0;
 #pragma unroll 1
@@ -1337,6 +1415,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
             if (trace) trace[step * NTRACE + 9] = globaltimer_ns() - t_start;
         }
 
+        if (WORLD > 1) {
+            // the collector warp finishes the step it is working on (its waits are bounded) before
+            // it is shown the stop flag
+            if (have_prev) {
+                const long long want = ((step_prev + 1) << 32) | 0x7fffffffLL;
+                while (*(volatile long long *)&ctl->qready < want) __nanosleep(32);
+            }
+            if (tid == 0) *(volatile int *)&ctl->hstop = 1;
+        }
         cbar();
         for (int i = tid; i < rows_c; i += NTC) p.r[row0 + i] = r_loc[i];
         if (c == 0 && tid == 0) {
@@ -1992,20 +2079,18 @@ static int plan_geometry(b200l_ctx *c) {
         const int o_colsum = take(2 * (4 + MAX_CS) * 16);         // gathered scalars + columns (+ group sums)
         const int o_small = take((2 * MAX_CS + 2 * NW) * 8);      // l1s, es, lsred
         const int o_qpart = take(rows_pad * 8);
-        const int qw_plan = (int)round_up(rows_max + 2, 2);
-        const int cell_bytes = c->world * qw_plan * 16;         // raw words of one exchange step
-        // few words to collect (at most one per thread): per-row sends and a polled gather are
-        // quicker than per-tile sends and a bulk-copy gather (dbg bits 8/9 force either)
-        const bool few = (c->world - 1) * (rows_max + 2) <= NTC;
-        const bool cell_in_slot = c->world > 1 && cell_bytes <= slot_bytes && !(c->dbg & 256) && (!few || (c->dbg & 512));
-        const int o_qx = take(c->world > 1 && !cell_in_slot ? (c->world - 1) * qw_plan * 8 : 16);
+        const int o_qx = take(16);
         const int o_tilecnt = take(128 * 4);
         if (out) {
             out->off_bar = o_bar; out->off_ctl = o_ctl; out->off_rloc = o_rloc; out->off_qloc = o_qloc;
             out->off_rT = o_rT; out->off_qT = o_qT; out->off_delta = o_delta; out->off_redT = o_redT;
             out->off_colsum = o_colsum; out->off_small = o_small; out->off_qpart = o_qpart;
             out->off_qx = o_qx; out->off_red2 = o_red2; out->off_tilecnt = o_tilecnt;
-            out->qx_words = cell_in_slot ? c->world * qw_plan : 0;
+            // multi-GPU send side: the collector warp sends the rows of a pass-2 tile when the
+            // consumer warps are done with it (row-major, up to 128 tiles); otherwise the lane that
+            // finishes a row stores it to every peer itself (also forced by dbg bit 8)
+            const int nt_plan = trans ? nt_t : (rows_max + TR - 1) / TR;
+            out->qx_words = (c->world > 1 && !trans && nt_plan <= 128 && !(c->dbg & 256)) ? 1 : 0;
         }
     };
     // the ring goes first (offset 0); sized after the fixed part is known
@@ -2076,7 +2161,8 @@ static int plan_geometry(b200l_ctx *c) {
         if (!fn) return fail("internal: no kernel for cpt=%d", cpt);
         CK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_bytes));
         int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, NTHREADS, c->smem_bytes));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, full ? NTHREADS_MG : NTHREADS,
+                                                         c->smem_bytes));
         if (occ < 1) return fail("fused kernel does not fit on an SM (smem=%d)", c->smem_bytes);
     }
     int coop = 0;
@@ -2091,7 +2177,7 @@ extern "C" int b200l_run_config(b200l_ctx *c, int32_t *grid, int32_t *threads, i
     if (need_A(c)) return 1;
     if (plan_geometry(c)) return 1;
     if (grid) *grid = c->grid;
-    if (threads) *threads = NTHREADS;
+    if (threads) *threads = c->world > 1 ? NTHREADS_MG : NTHREADS;
     if (smem_bytes) *smem_bytes = c->smem_bytes;
     if (tile_rows) *tile_rows = c->geo.TR;
     if (ring_slots) *ring_slots = c->geo.S;
@@ -2171,7 +2257,7 @@ static int launch_fused(b200l_ctx *c, const int32_t *order_host, int64_t nsteps,
     fused_fn fn = ctx_kernel(c, c->world > 1 || trace_dev != nullptr || ttrace_dev != nullptr || (c->dbg & 7) != 0);
     void *args[] = {(void *)&p, (void *)&c->tmap};
     if (timed) CK(cudaEventRecord(c->ev0, c->stream));
-    CK(cudaLaunchCooperativeKernel((const void *)fn, dim3(c->grid), dim3(NTHREADS), args,
+    CK(cudaLaunchCooperativeKernel((const void *)fn, dim3(c->grid), dim3(c->world > 1 ? NTHREADS_MG : NTHREADS), args,
                                    (size_t)c->smem_bytes, c->stream));
     if (timed) CK(cudaEventRecord(c->ev1, c->stream));
     c->step_counter += nsteps;

@@ -23,9 +23,13 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    cases = [(300, 2400, 4, 0.05, "double", 7), (257, 1024 * world, 8, 0.03, "double", 11),
-             (1000, 8000, 2, 0.02, "float", 5), (64, 64 * world, 1, 0.2, "double", 3)]
-    for (N, K, BLOCK, den, TYPE, seed) in cases:
+    # (N, K, BLOCK, density, type, seed, layout); N = 12000 gives 81-82 rows per CTA: the collector
+    # warp needs two batches and pass 1 of the next step waits on single tiles
+    cases = [(300, 2400, 4, 0.05, "double", 7, "row"), (257, 1024 * world, 8, 0.03, "double", 11, "row"),
+             (1000, 8000, 2, 0.02, "float", 5, "row"), (64, 64 * world, 1, 0.2, "double", 3, "row"),
+             (12000, 64 * world, 2, 0.1, "double", 13, "row"), (600, 1600, 2, 0.05, "double", 17, "transposed"),
+             (1200, 2400, 3, 0.04, "float", 19, "transposed")]
+    for (N, K, BLOCK, den, TYPE, seed, LAYOUT) in cases:
         A, _, b, mu = orc.make_problem(N, K, den, seed=seed)
         if TYPE == "float":
             A = A.astype(np.float32).astype(np.float64)
@@ -38,6 +42,7 @@ def main():
         class Cal(GPU_Calculation):
             pass
         Cal.TYPE = TYPE
+        Cal.LAYOUT = LAYOUT
         Cal.DEVICE = local
         A_loc = dd.shard_columns(A, BLOCK, rank, world)
         cal = Cal(A_loc, BLOCK)
@@ -61,8 +66,8 @@ def main():
         good = bool(rel < tol and same_iters and supp and errs < max(tol, 1e-10) and same_trace)
         ok = ok and good
         if rank == 0:
-            print("case N=%d K=%d BLOCK=%d %s world=%d: iters %d/%d rel %.2e err-trace %.2e support %s same-trace %s -> %s"
-                  % (N, K, BLOCK, TYPE, world, solver.iters, o["iters"], rel, errs, supp, same_trace,
+            print("case N=%d K=%d BLOCK=%d %s %s world=%d: iters %d/%d rel %.2e err-trace %.2e support %s same-trace %s -> %s"
+                  % (N, K, BLOCK, TYPE, LAYOUT, world, solver.iters, o["iters"], rel, errs, supp, same_trace,
                      "ok" if good else "FAIL"))
         dd.disconnect(cal)
         del solver, cal

@@ -33,17 +33,31 @@ def main():
     ap.add_argument("--sweep", default="", help="semicolon list of slot,inflight[,dbg] tuples")
     ap.add_argument("--out", default="")
     ap.add_argument("--raw", default="", help="prefix for raw trace dumps (.npy)")
+    ap.add_argument("--tiles", action="store_true", help="per-tile durations of the two passes")
     args = ap.parse_args()
     N, K, BLOCK = args.N, args.K, args.block
+    # under torchrun: one C2-sized column shard per rank (the instance grows with the world size)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
 
     class Cal(GPU_Calculation):
         TYPE = args.dtype
         LAYOUT = args.layout
-    dev = torch.device("cuda", 0)
+        DEVICE = local_rank
+    dev = torch.device("cuda", local_rank)
     tdt = torch.float32 if args.dtype == "float" else torch.float64
     ld = Cal.padded_ld(N, K, BLOCK)
-    store, b, mu = make_device_instance(torch, dev, N, K, BLOCK, 0.01, 2, tdt, ld, args.layout)
+    store, b, mu = make_device_instance(torch, dev, N, K, BLOCK, 0.01, 2, tdt, ld, args.layout, dist, rank)
     cal = Cal.from_device_blocks(store, N, K, BLOCK)
+    if world > 1:
+        from convex_optimization_b200 import distributed as dd
+        dd.connect(cal)
     lib, ctx = cal._lib, cal.ctx
     bb = np.ascontiguousarray(b.reshape(-1))
     NT = _lib.NTRACE
@@ -65,7 +79,7 @@ def main():
         tr = np.zeros((G, nsteps, NT), np.uint64)
         kms = ctypes.c_double()
         g_out = ctypes.c_int32()
-        tt = np.zeros((G, nsteps, _lib.NTTRACE), np.uint64) if args.raw else None
+        tt = np.zeros((G, nsteps, _lib.NTTRACE), np.uint64) if (args.raw or args.tiles) else None
         _lib.check(lib.b200l_run_traced(ctx, nsteps, float(mu),
                                         tr.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)),
                                         tt.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)) if tt is not None else None,
@@ -99,15 +113,34 @@ def main():
                 "column sums": round(float((f[:, :, 14] - f[:, :, 13]).mean()), 3),
                 "closing barrier": round(float((f[:, :, 3] - f[:, :, 14]).mean()), 3),
                 "fetches per step": round(float(tr[:, BLOCK:, 11].mean()), 3)}
+        if world > 1 and NT >= 16:
+            f = tr.astype(np.float64)[:, BLOCK:, :] * 1e-3
+            out["peer_rows_us"] = {
+                "pass 2 end -> all peer rows summed (collector warp)": round(float((f[:, :, 15] - f[:, :, 8]).mean()), 3),
+                "max over CTAs": round(float((f[:, :, 15] - f[:, :, 8]).max(axis=0).mean()), 3)}
+        if args.tiles:
+            ft = tt.astype(np.float64)[:, BLOCK:, :] * 1e-3
+            ntile = min(16, geo["tiles_per_slab"])
+            out["tiles_us"] = {
+                "pass1 tile (data landed -> done, incl. wait for peer rows)":
+                    [round(float((ft[:, :, 16 + t] - ft[:, :, t]).mean()), 3) for t in range(ntile)],
+                "pass1 tile end -> next tile landed":
+                    [round(float((ft[:, :, t + 1] - ft[:, :, 16 + t]).mean()), 3) for t in range(ntile - 1)],
+                "pass2 tile": [round(float((ft[:, :, 48 + t] - ft[:, :, 32 + t]).mean()), 3) for t in range(ntile)]}
         results.append(out)
         if args.raw:
             np.save("%s_%d_%d_%d.npy" % (args.raw, slot, infl, dbg), tr)
             np.save("%s_tiles_%d_%d_%d.npy" % (args.raw, slot, infl, dbg), tt[::16])
-        print(json.dumps({k: out[k] for k in ("tuning", "ms_per_sweep", "sweeps_per_s", "us_per_block_step",
-                                               "phases_us_mean_over_ctas", "skew_us_pass1_end", "gather_g_detail_us") if k in out}))
+        if rank == 0:
+            print(json.dumps({k: out[k] for k in ("tuning", "ms_per_sweep", "sweeps_per_s", "us_per_block_step",
+                                                   "phases_us_mean_over_ctas", "skew_us_pass1_end",
+                                                   "gather_g_detail_us", "peer_rows_us", "tiles_us") if k in out}))
         sys.stdout.flush()
     out = results if len(results) > 1 else results[0]
-    if args.out:
+    if world > 1:
+        dd.disconnect(cal)
+        dist.destroy_process_group()
+    if args.out and rank == 0:
         with open(args.out, "w") as f:
             json.dump(out, f, indent=1)
 
