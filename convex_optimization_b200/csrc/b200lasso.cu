@@ -371,6 +371,34 @@ struct Waiter {
     }
 };
 
+// Exchange fetches land as one bulk copy; words that had not been written yet when the copy
+// read them are repaired one by one: thread `tid` owns the words tid + NTC*i of the landing
+// area (bit i of `mask` = still missing), re-reads them from L2, up to four in flight, until
+// their tags match, and patches the landing area.  No second bulk copy, no CTA-wide retry.
+__device__ __noinline__ void ll_repair(ulonglong2 *stage, const ulonglong2 *srcw, int tid, unsigned mask,
+                                       uint32_t tag, Waiter &waiter) {
+    while (mask) {
+        unsigned m = mask;
+        while (m) {
+            const int i0 = __ffs(m) - 1;
+            m &= m - 1;
+            const int i1 = m ? __ffs(m) - 1 : i0;
+            m &= m - 1;
+            const int i2 = m ? __ffs(m) - 1 : i0;
+            m &= m - 1;
+            const int i3 = m ? __ffs(m) - 1 : i0;
+            m &= m - 1;
+            const int e0 = tid + NTC * i0, e1 = tid + NTC * i1, e2 = tid + NTC * i2, e3 = tid + NTC * i3;
+            const ulonglong2 v0 = ll_ld(srcw + e0), v1 = ll_ld(srcw + e1), v2 = ll_ld(srcw + e2), v3 = ll_ld(srcw + e3);
+            if (ll_ok(v0, tag)) { stage[e0] = v0; mask &= ~(1u << i0); }
+            if (ll_ok(v1, tag)) { stage[e1] = v1; mask &= ~(1u << i1); }
+            if (ll_ok(v2, tag)) { stage[e2] = v2; mask &= ~(1u << i2); }
+            if (ll_ok(v3, tag)) { stage[e3] = v3; mask &= ~(1u << i3); }
+        }
+        if (mask && !waiter.again()) break;
+    }
+}
+
 // load 4 consecutive entries of a T vector in shared memory (16-byte aligned for float)
 __device__ __forceinline__ void load4(const float *p, float (&v)[4]) {
     const float4 t = *reinterpret_cast<const float4 *>(p);
@@ -1031,34 +1059,30 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                     const int gn = min(p.gc, G - g0);
                     const ulonglong2 *srcw = inbox + (size_t)g0 * MW;
                     const int nwords = gn * MW;
-                    int nfetch = 0;
-                    for (;;) {
-                        if (tid == 0) {
-                            mbar_expect_tx(xbar, (uint32_t)nwords * 16u);
-                            tma_bulk_g2s(stage, srcw, (uint32_t)nwords * 16u, xbar);
-                            if (p.gate_mode == 1) *(volatile long long *)&ctl->gate = step + 1;
-                        }
-                        mbar_wait(xbar, xphase);
-                        xphase ^= 1u;
-                        if (trace && !drain && nfetch == 0) trace[step * NTRACE + 10] = globaltimer_ns() - t_start;
-                        ++nfetch;
-                        if (trace && !drain) trace[step * NTRACE + 11] = nfetch;
-                        int bad = -1;
-#pragma unroll 2
-                        for (int e = tid; e < nwords; e += NTC)
-                            if (!ll_ok(stage[e], tag)) bad = e;
-                        if (trace && !drain) trace[step * NTRACE + 12] = globaltimer_ns() - t_start;
-                        const bool anybad = cbar_or(bad >= 0);
-                        if (trace && !drain) trace[step * NTRACE + 13] = globaltimer_ns() - t_start;
-                        if (!anybad || (DBG & 1)) break;
-                        if (bad >= 0) {
-                            waiter.begin(((long long)step << 32) | ((long long)(g0 * MW + bad) & 0xffffffff));
-                            while (!ll_ok(ll_ld(srcw + bad), tag)) {
-                                if (!waiter.again()) break;
-                            }
-                        }
-                        if (cbar_or(*(volatile int *)&ctl->abort != 0)) break;
+                    if (tid == 0) {
+                        mbar_expect_tx(xbar, (uint32_t)nwords * 16u);
+                        tma_bulk_g2s(stage, srcw, (uint32_t)nwords * 16u, xbar);
+                        if (p.gate_mode == 1) *(volatile long long *)&ctl->gate = step + 1;
                     }
+                    mbar_wait(xbar, xphase);
+                    xphase ^= 1u;
+                    if (trace && !drain) trace[step * NTRACE + 10] = globaltimer_ns() - t_start;
+                    unsigned missing = 0;
+                    {
+                        int i = 0;
+#pragma unroll 2
+                        for (int e = tid; e < nwords; e += NTC, ++i)
+                            if (!ll_ok(stage[e], tag)) missing |= 1u << i;
+                    }
+                    if (trace && !drain) trace[step * NTRACE + 11] = __popc(missing);
+                    if (missing && !(DBG & 1)) {
+                        waiter.begin(((long long)step << 32) | ((long long)(g0 * MW + tid) & 0xffffffff));
+                        ll_repair(stage, srcw, tid, missing, tag, waiter);
+                    }
+                    if (trace && !drain) trace[step * NTRACE + 12] = globaltimer_ns() - t_start;
+                    const bool gab = cbar_or(*(volatile int *)&ctl->abort != 0);   // repaired words visible
+                    if (trace && !drain) trace[step * NTRACE + 13] = globaltimer_ns() - t_start;
+                    if (gab) break;
                     // column sums: warp = a pair of adjacent message words (2pr, 2pr+1), lane =
                     // (source lane/2 + 16i, word lane%2).  The message length is 2 (mod 4) words, so
                     // the 8 lanes of a quarter warp hit 8 different 16-byte bank groups.  Straight-line
@@ -1195,26 +1219,24 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                     const int nwords = min(p.dchunk, dtot - w0);
                     const ulonglong2 *srcw = p.dLL + w0;
                     if (w0 > 0) cbar();            // the previous chunk has been decoded
-                    for (;;) {
-                        if (tid == 0) {
-                            mbar_expect_tx(xbar, (uint32_t)nwords * 16u);
-                            tma_bulk_g2s(stage, srcw, (uint32_t)nwords * 16u, xbar);
-                            if (p.gate_mode == 3) *(volatile long long *)&ctl->gate = step + 1;
-                        }
-                        mbar_wait(xbar, xphase);
-                        xphase ^= 1u;
-                        int bad = -1;
+                    if (tid == 0) {
+                        mbar_expect_tx(xbar, (uint32_t)nwords * 16u);
+                        tma_bulk_g2s(stage, srcw, (uint32_t)nwords * 16u, xbar);
+                        if (p.gate_mode == 3) *(volatile long long *)&ctl->gate = step + 1;
+                    }
+                    mbar_wait(xbar, xphase);
+                    xphase ^= 1u;
+                    // every thread checks, repairs and then decodes its own words: no vote needed
+                    unsigned missing = 0;
+                    {
+                        int i = 0;
 #pragma unroll 4
-                        for (int e = tid; e < nwords; e += NTC)
-                            if (!ll_ok(stage[e], tag)) bad = e;
-                        if (!cbar_or(bad >= 0) || (DBG & 1)) break;
-                        if (bad >= 0) {
-                            waiter.begin(((long long)step << 32) | (1LL << 31) | (long long)(w0 + bad));
-                            while (!ll_ok(ll_ld(srcw + bad), tag)) {
-                                if (!waiter.again()) break;
-                            }
-                        }
-                        if (cbar_or(*(volatile int *)&ctl->abort != 0)) break;
+                        for (int e = tid; e < nwords; e += NTC, ++i)
+                            if (!ll_ok(stage[e], tag)) missing |= 1u << i;
+                    }
+                    if (missing && !(DBG & 1)) {
+                        waiter.begin(((long long)step << 32) | (1LL << 31) | (long long)(w0 + tid));
+                        ll_repair(stage, srcw, tid, missing, tag, waiter);
                     }
 #pragma unroll 4
                     for (int e = tid; e < nwords; e += NTC)
@@ -1271,7 +1293,10 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
             if (tid == 0) {                // my l1 / err terms of this step travel with the rows
                 send_row(rows_c, ctl->sp[2]);
                 send_row(rows_c + 1, ctl->sp[3]);
-                if (WORLD > 1) *(volatile long long *)&ctl->p2start = step + 1;
+                if (WORLD > 1) {
+                    __threadfence_block();
+                    *(volatile long long *)&ctl->p2start = step + 1;
+                }
             }
 
             // ---------------- pass 2: q = A_m D over the slab ---------------------------

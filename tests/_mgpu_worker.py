@@ -57,7 +57,9 @@ def main():
         big = np.abs(o["x"]) > 1e-5 * np.abs(o["x"]).max()
         supp = np.array_equal(x != 0, o["x"] != 0) if TYPE == "double" else np.array_equal((x != 0)[big], (o["x"] != 0)[big])
         n = min(solver.iters, o["iters"])
-        errs = np.abs(err_iter[:n] - o["err"][:n]).max()
+        # error trace relative to its scale (the entries grow with N; the sums over 8 ranks and
+        # 148 CTAs are ordered differently from the oracle's)
+        errs = np.abs(err_iter[:n] - o["err"][:n]).max() / max(1.0, np.abs(o["err"][:n]).max())
         # every rank must hold bitwise the same trace (replicated r and gamma)
         t = torch.from_numpy(err_iter.copy()).cuda()
         parts = [torch.empty_like(t) for _ in range(world)]
