@@ -60,7 +60,7 @@ static int fail(const char *fmt, ...) {
 constexpr int NW = 8;                  // consumer warps
 constexpr int NTC = NW * 32;           // consumer threads
 constexpr int NTHREADS = NTC + 32;     // + one producer warp
-constexpr int NTHREADS_MG = NTC + 64;  // multi-GPU: + one warp that collects the peers' rows
+constexpr int NTHREADS_MG = NTC + 96;  // multi-GPU: + a warp that sends my partial rows and one that collects the peers'
 constexpr int MAX_CS = 64;             // max stage-2 slice width (columns per CTA)
 
 template <typename T> struct VT;
@@ -290,6 +290,8 @@ struct Ctl {
     long long gate;                  // steps whose pass-2 copies the producer may issue
     long long qready;                // multi-GPU: (step + 1) << 32 | rows of A_m D summed over the ranks
     long long p2start, p2done;       // multi-GPU: steps whose pass 2 (my partial rows) has begun / is complete
+    long long own_rows;              // multi-GPU: (step + 1) << 32 | my rows that are final (and sent)
+    double qsc[2];                   // multi-GPU: l1 / err terms summed over the ranks (until the step is complete)
     int hstop;                       // multi-GPU: the consumers are done, the collector warp exits
     unsigned long long t_start;      // time base of the phase trace
 };
@@ -557,6 +559,7 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
         ctl->qready = 0;
         ctl->p2done = 0;
         ctl->p2start = 0;
+        ctl->own_rows = 0;
         ctl->hstop = 0;
         for (int i = 0; i < 128; ++i) tilecnt[i] = 0;
         ctl->kc = 0;
@@ -642,15 +645,70 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
         }
         __syncwarp();
     } else if (wid == NW + 1) {
+        // ============== multi-GPU: sender of my partial A_m D ======================
+        // My partial rows go to the peers tile by tile, as soon as the 8 consumer warps are done
+        // with a pass-2 tile: consecutive lanes = consecutive words (whole NVLink packets), and
+        // the peer stores stay out of the inner loop of pass 2.  (TRANS, or more tiles than
+        // counters: the consumers send their rows themselves.)
+        if (WORLD > 1 && p.xmode == 0) {
+            Waiter hw{p.abort_flag, &ctl->abort, p.wait_limit_ns, 0u, 0ull, p.state + 4, 0};
+            bool live = true;
+            for (long long hs = 0; live; ++hs) {
+                const uint32_t tag = p.tag_base + (uint32_t)hs + 1u;
+                unsigned spin = 0;
+                while (!__all_sync(0xffffffffu, *(volatile long long *)&ctl->p2start > hs)) {
+                    if (__any_sync(0xffffffffu, *(volatile int *)&ctl->hstop != 0)) {
+                        live = false;
+                        break;
+                    }
+                    __nanosleep(64);
+                }
+                if (!live) break;
+                hw.begin((hs << 32) | (3LL << 30));
+                const size_t mine = (((size_t)(tag & 1u) * G + c) * WORLD + p.rank) * p.qw;
+                __threadfence_block();
+                if (lane < 2) {                // l1 and err terms of my columns (set before pass 2)
+                    const double v = ctl->sp[2 + lane];
+#pragma unroll 1
+                    for (int pr = 0; pr < WORLD; ++pr)
+                        if (pr != p.rank) ll_st_dbl(p.peer[pr] + mine + rows_c + lane, v, tag);
+                }
+#pragma unroll 1
+                for (int t = 0; t < nt; ++t) {
+                    // (naps: this warp shares its scheduler with two consumer warps)
+                    while (!__all_sync(0xffffffffu, *(volatile int *)&tilecnt[t & 127] >= NW)) {
+                        __nanosleep(100);
+                        if ((++spin & 63u) == 0u && !__all_sync(0xffffffffu, hw.again())) break;
+                    }
+                    __threadfence_block();
+                    const int rows_t = min(TR, rows_c - t * TR);
+#pragma unroll 1
+                    for (int i = lane; i < rows_t; i += 32) {
+                        const double v = qpart[t * TR + i];
+#pragma unroll 1
+                        for (int pr = 0; pr < WORLD; ++pr)
+                            if (pr != p.rank) ll_st_dbl(p.peer[pr] + mine + t * TR + i, v, tag);
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        tilecnt[t & 127] = 0;
+                        // my rows of this tile are final: the collector may add them up
+                        *(volatile long long *)&ctl->own_rows = ((hs + 1) << 32) | (long long)min((t + 1) * TR, rows_c);
+                    }
+                }
+            }
+        }
+    } else if (wid == NW + 2) {
         // ============== multi-GPU: collector of the peers' partial A_m D ===========
         // (the reduce of lasso.py:126 over the reference's P column slices).  CTA c of every
         // rank owns the same rows; during pass 2 each rank stores its finished rows (and its
         // l1 / err terms) as tagged words straight into the inbox of CTA c on every peer
-        // (NVLink peer stores).  This warp collects them while the consumers already run
-        // pass 1 of the next step -- which needs the summed rows tile by tile, in the order
-        // they were sent -- so the NVLink latency hides behind the streaming.  Sums in rank
-        // order: every rank holds bitwise the same q, gamma and r.  Cells are double-buffered
-        // by step parity: a rank can be at most one exchange ahead.
+        // (NVLink peer stores).  This warp polls them from the start of pass 2 and, while the
+        // consumers already run pass 1 of the next step -- which needs the summed rows tile by
+        // tile, in the order they were sent --, releases every row as soon as all ranks' parts
+        // are there: the NVLink latency hides behind the streaming.  Sums in rank order: every
+        // rank holds bitwise the same q, gamma and r.  Cells are double-buffered by step parity:
+        // a rank can be at most one exchange ahead.
         if (WORLD > 1) {
             Waiter hw{p.abort_flag, &ctl->abort, p.wait_limit_ns, 0u, 0ull, p.state + 4, 0};
             const int nq = rows_c + 2;                       // rows, then the l1 and err terms
@@ -659,7 +717,7 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                 const uint32_t tag = p.tag_base + (uint32_t)hs + 1u;
                 const ulonglong2 *mycell = p.peer[p.rank] + (((size_t)(tag & 1u) * G + c) * WORLD) * p.qw;
                 double trq = 0.0, tqq = 0.0;
-                bool own_ready = false;                      // my own pass 2 of step hs is complete
+                int own_rows = 0;                            // my own rows below this index are final
                 unsigned spin = 0;
                 // nothing can arrive before the ranks are in pass 2 of this step: nap until mine
                 // begins (shared-memory flag, no L2 traffic)
@@ -672,32 +730,6 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                 }
                 if (!live) break;
                 hw.begin((hs << 32) | (2LL << 30));
-                if (p.xmode == 0) {
-                    // my partial rows go to the peers tile by tile, as soon as the 8 consumer warps are
-                    // done with a tile: consecutive lanes = consecutive words (whole NVLink packets),
-                    // and the stores stay out of the inner loop of pass 2
-                    const size_t mine = (((size_t)(tag & 1u) * G + c) * WORLD + p.rank) * p.qw;
-#pragma unroll 1
-                    for (int t = 0; t < nt; ++t) {
-                        while (!__all_sync(0xffffffffu, *(volatile int *)&tilecnt[t & 127] >= NW)) {
-                            if (!__all_sync(0xffffffffu, hw.again())) break;
-                        }
-                        __threadfence_block();
-                        const int rows_t = min(TR, rows_c - t * TR);
-#pragma unroll 1
-                        for (int i = lane; i < rows_t; i += 32) {
-                            const double v = qpart[t * TR + i];
-#pragma unroll 1
-                            for (int pr = 0; pr < WORLD; ++pr)
-                                if (pr != p.rank) ll_st_dbl(p.peer[pr] + mine + t * TR + i, v, tag);
-                        }
-                        __syncwarp();
-                        if (lane == 0) tilecnt[t & 127] = 0;
-                        if (DBG & 1024) __threadfence_system();
-                    }
-                    own_ready = true;
-                    __threadfence_block();
-                }
 #pragma unroll 1
                 for (int i0 = 0; i0 < nq && live; i0 += 64) {        // 2 x 32 words x (world-1) sources in flight
                     ulonglong2 w[2][B200L_MAX_WORLD - 1];
@@ -711,15 +743,18 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                             if (k < WORLD - 1)
                                 w[h][k] = ll_ld(mycell + (size_t)(k < p.rank ? k : k + 1) * p.qw + min(i, nq - 1));
                     }
-                    // the peers' words are polled from the moment the previous step is finished; a
-                    // row is summed (rank order) and released to pass 1 as soon as it is complete
-                    // and every row before it is
                     for (;;) {
-                        if (!own_ready) {
-                            own_ready = __all_sync(0xffffffffu, *(volatile long long *)&ctl->p2done > hs);
-                            if (own_ready) {
+                        if (own_rows < rows_c) {
+                            // final rows of my own partial product: all of them once pass 2 is
+                            // complete, else what the sender warp has sent
+                            const long long pd = *(volatile long long *)&ctl->p2done;
+                            const long long orw = *(volatile long long *)&ctl->own_rows;
+                            int mine_n = pd > hs ? rows_c : ((orw >> 32) == hs + 1 ? (int)(orw & 0x7fffffff) : 0);
+                            mine_n = __reduce_min_sync(0xffffffffu, mine_n);
+                            if (mine_n > own_rows) {
+                                own_rows = mine_n;
                                 __threadfence_block();
-                            } else if (__any_sync(0xffffffffu, *(volatile int *)&ctl->hstop != 0)) {
+                            } else if (mine_n == 0 && __any_sync(0xffffffffu, *(volatile int *)&ctl->hstop != 0)) {
                                 live = false;                // the consumers are gone: no step hs
                                 break;
                             }
@@ -736,7 +771,7 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                                         w[h][k] = ll_ld(mycell + (size_t)(k < p.rank ? k : k + 1) * p.qw + i);
                                     }
                                 }
-                                if (ok && own_ready) {
+                                if (ok && (i < own_rows || i >= rows_c)) {
                                     const double own = i < rows_c ? qpart[i] : ctl->sp[2 + (i - rows_c)];
                                     const bool is_max = i == rows_c + 1;
                                     double acc = 0.0;
@@ -754,7 +789,7 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                                         trq += r_loc[i] * acc;                           // lasso.py:129
                                         tqq += acc * acc;                                // lasso.py:132
                                     } else {
-                                        ctl->sp[2 + (i - rows_c)] = acc;
+                                        ctl->qsc[i - rows_c] = acc;
                                     }
                                     done[h] = true;
                                 }
@@ -776,9 +811,12 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                 if (!live) break;
                 trq = warp_sum(trq);
                 tqq = warp_sum(tqq);
+                __syncwarp();
                 if (lane == 0) {
                     ctl->sp[0] = trq;
                     ctl->sp[1] = tqq;
+                    ctl->sp[2] = ctl->qsc[0];
+                    ctl->sp[3] = ctl->qsc[1];
                     __threadfence_block();
                     *(volatile long long *)&ctl->qready = ((hs + 1) << 32) | 0x7fffffffLL;
                     if (p.trace)
@@ -1290,13 +1328,13 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                         if (pr != p.rank) ll_st_dbl(p.peer[pr] + cell + (size_t)p.rank * p.qw + idx, v, tag);
                 }
             };
-            if (tid == 0) {                // my l1 / err terms of this step travel with the rows
-                send_row(rows_c, ctl->sp[2]);
-                send_row(rows_c + 1, ctl->sp[3]);
-                if (WORLD > 1) {
-                    __threadfence_block();
-                    *(volatile long long *)&ctl->p2start = step + 1;
+            if (WORLD > 1 && tid == 0) {   // my l1 / err terms of this step travel with the rows
+                if (p.xmode == 1) {        // (otherwise the collector warp sends them)
+                    send_row(rows_c, ctl->sp[2]);
+                    send_row(rows_c + 1, ctl->sp[3]);
                 }
+                __threadfence_block();
+                *(volatile long long *)&ctl->p2start = step + 1;
             }
 
             // ---------------- pass 2: q = A_m D over the slab ---------------------------
@@ -1703,7 +1741,7 @@ extern "C" int b200l_ctx_create(b200l_ctx **out, int dtype, int layout, int64_t 
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = (int)prop.sharedMemPerBlockOptin;
     c->l2_bytes = prop.l2CacheSize;
-    c->slot_target = 65536;
+    c->slot_target = 0;
     c->max_inflight = 0;
     c->wait_limit_ns = 5000000000ULL;
     c->world = 1;
@@ -1990,7 +2028,7 @@ extern "C" int b200l_objective(b200l_ctx *c, double mu, double *value) {
 // ------------------------------------------------------------------------------------
 extern "C" int b200l_set_tuning(b200l_ctx *c, int32_t slot_bytes_target, int32_t max_inflight_tiles) {
     if (!c) return fail("ctx is NULL");
-    c->slot_target = slot_bytes_target > 0 ? slot_bytes_target : 65536;
+    c->slot_target = slot_bytes_target > 0 ? slot_bytes_target : 0;   // 0: chosen per shape
     c->max_inflight = max_inflight_tiles;
     c->geo_valid = 0;
     return 0;
@@ -2066,7 +2104,12 @@ static int plan_geometry(b200l_ctx *c) {
     if (cpt > 8) return fail("internal: cpt=%d", cpt);
     const int nrg = (!trans && cpt == 1) ? std::max(1, NTC / ncg) : 1;
     // rows per tile: as many as fit the slot target, whole quads when possible, at most 64
-    int TR = (int)std::min<int64_t>(64, std::max<int64_t>(1, c->slot_target / rowbytes));
+    // default tile size (measured): blocks that stay in L2 between the passes (C2: 40 MB) are
+    // bound by the exchanges and like 48 KB tiles and one more ring slot; blocks that stream from
+    // HBM in both passes (C3, C4: 250-320 MB) like 64 KB tiles
+    const bool l2_resident = 2 * (int64_t)c->brows * c->ld * es <= (int64_t)c->l2_bytes * 3 / 4;
+    const int64_t slot_target = c->slot_target > 0 ? c->slot_target : (l2_resident && !trans ? 49152 : 65536);
+    int TR = (int)std::min<int64_t>(64, std::max<int64_t>(1, slot_target / rowbytes));
     TR = std::min(TR, (int)round_up(std::max(rows_max, 1), 4));
     if (TR >= 4) TR &= ~3;
     // transposed layout: box of BX residual entries (odd number of 16-byte groups) x TJ columns

@@ -132,8 +132,9 @@ int b200l_set_tuning(b200l_ctx *ctx, int32_t slot_bytes_target, int32_t max_infl
  * done, [2] partial gradient published, [3] my columns gathered, [4] partials combined,
  * [5] pending step resolved (gamma), [6] prox done / D published, [7] D gathered,
  * [8] pass 2 (A_m D) done, [9] line-search partials done, [10] first inbox fetch landed,
- * [11] number of inbox fetches of the step, [12] inbox tags checked, [13] barrier after the
- * check, [14] column sums done.  trace_host holds
+ * [11] inbox words thread 0 had to re-read from L2, [12] inbox tags checked and missing words
+ * repaired, [13] barrier after that, [14] column sums done, [15] multi-GPU: the peers' rows of
+ * this step summed.  trace_host holds
  * grid*nsteps*B200L_NTRACE uint64 (grid = b200l_run_config's grid, also returned in grid_out).
  * No counterpart in the reference (its only timer is lasso.py:234-236). */
 int b200l_run_traced(b200l_ctx *ctx, int64_t nsteps, double mu, uint64_t *trace_host,

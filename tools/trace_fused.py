@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--raw", default="", help="prefix for raw trace dumps (.npy)")
     ap.add_argument("--tiles", action="store_true", help="per-tile durations of the two passes")
+    ap.add_argument("--all-ranks", action="store_true", help="under torchrun: every rank prints its line")
     args = ap.parse_args()
     N, K, BLOCK = args.N, args.K, args.block
     # under torchrun: one C2-sized column shard per rank (the instance grows with the world size)
@@ -107,12 +108,12 @@ def main():
         if NT >= 15:        # inside "gather g": fetch landed, tags checked, barrier, column sums (last fetch)
             f = tr.astype(np.float64)[:, BLOCK:, :] * 1e-3
             out["gather_g_detail_us"] = {
-                "publish end -> first fetch landed": round(float((f[:, :, 10] - f[:, :, 2]).mean()), 3),
-                "fetch landed -> tags checked (incl. refetches)": round(float((f[:, :, 12] - f[:, :, 10]).mean()), 3),
+                "publish end -> inbox fetch landed": round(float((f[:, :, 10] - f[:, :, 2]).mean()), 3),
+                "tags checked, missing words repaired from L2": round(float((f[:, :, 12] - f[:, :, 10]).mean()), 3),
                 "barrier": round(float((f[:, :, 13] - f[:, :, 12]).mean()), 3),
                 "column sums": round(float((f[:, :, 14] - f[:, :, 13]).mean()), 3),
                 "closing barrier": round(float((f[:, :, 3] - f[:, :, 14]).mean()), 3),
-                "fetches per step": round(float(tr[:, BLOCK:, 11].mean()), 3)}
+                "words repaired per thread and step": round(float(tr[:, BLOCK:, 11].mean()), 3)}
         if world > 1 and NT >= 16:
             f = tr.astype(np.float64)[:, BLOCK:, :] * 1e-3
             out["peer_rows_us"] = {
@@ -127,14 +128,26 @@ def main():
                 "pass1 tile end -> next tile landed":
                     [round(float((ft[:, :, t + 1] - ft[:, :, 16 + t]).mean()), 3) for t in range(ntile - 1)],
                 "pass2 tile": [round(float((ft[:, :, 48 + t] - ft[:, :, 32 + t]).mean()), 3) for t in range(ntile)]}
+            # the tile stamps are absolute, the phase stamps relative to the kernel start of the CTA
+            fp = tr.astype(np.float64)[:, BLOCK:, :] * 1e-3
+            off = ft[:, :, 16 + ntile - 1] - fp[:, :, 1]
+            out["tiles_us"]["pass2 tile 0 issued by the producer, after the end of gather g"] = \
+                round(float((ft[:, :, 80] - off - fp[:, :, 3]).mean()), 3)
+            out["tiles_us"]["pass2 tile 0 landed, after the end of gather D"] = \
+                round(float((ft[:, :, 32] - off - fp[:, :, 7]).mean()), 3)
+            out["tiles_us"]["pass2 tile 0 landed, after its issue"] = round(float((ft[:, :, 32] - ft[:, :, 80]).mean()), 3)
+            out["tiles_us"]["pass2 tile end -> next tile start"] = \
+                [round(float((ft[:, :, 32 + t + 1] - ft[:, :, 48 + t]).mean()), 3) for t in range(ntile - 1)]
         results.append(out)
         if args.raw:
             np.save("%s_%d_%d_%d.npy" % (args.raw, slot, infl, dbg), tr)
             np.save("%s_tiles_%d_%d_%d.npy" % (args.raw, slot, infl, dbg), tt[::16])
-        if rank == 0:
+        if world > 1:
+            out["rank"] = rank
+        if rank == 0 or args.all_ranks:
             print(json.dumps({k: out[k] for k in ("tuning", "ms_per_sweep", "sweeps_per_s", "us_per_block_step",
                                                    "phases_us_mean_over_ctas", "skew_us_pass1_end",
-                                                   "gather_g_detail_us", "peer_rows_us", "tiles_us") if k in out}))
+                                                   "gather_g_detail_us", "peer_rows_us", "tiles_us", "rank") if k in out}))
         sys.stdout.flush()
     out = results if len(results) > 1 else results[0]
     if world > 1:
