@@ -67,51 +67,84 @@ def ncu_traffic(config, layout):
 
 # ------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled from a thread
+    every ~2 ms (nvidia_ml_py), nvidia-smi -lms as a fallback."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.rows = []          # (time, sm_mhz, max_mhz, [reasons])
         self.proc = None
+        self.nvml = None
+        self.stop_flag = False
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2] or [r for (_, r) in self.rows]
-        for r in rows:
-            f = [x.strip() for x in r.split(",")]
+    def _poll(self):
+        nv = self.nvml
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((time.time(), sm, self.max_mhz, [n for n, b in bits.items() if mask & b]))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _pump(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.strip().split(",")]
+            try:
+                self.rows.append((time.time(), float(f[0]), float(f[1]),
+                                  [n for n, v in zip(names, f[2:6]) if v.lower().startswith("active")]))
             except Exception:
                 continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self, t0, t1):
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml / nvidia-smi unavailable"], "samples": 0}
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+        else:
+            time.sleep(0.05)
+            self.proc.terminate()
+        # NVML queries can stall while the process sits in a stream synchronisation, so samples
+        # up to 10 ms before / after the region count as "during" (clocks do not move that fast)
+        inside = [r for r in self.rows if t0 - 0.010 <= r[0] <= t1 + 0.010]
+        rows = inside or self.rows          # (a region shorter than the sampling period: nearest samples)
+        reasons = sorted({n for r in rows for n in r[3]})
+        return {"sm_mhz": float(np.median([r[1] for r in rows])) if rows else None,
+                "sm_max_mhz": float(max(r[2] for r in rows)) if rows else None,
+                "reasons": reasons, "samples": len(inside),
+                "source": "nvml, 2 ms period" if self.nvml is not None else "nvidia-smi -lms 20"}
 
 
 # ------------------------------------------------------------------------------ data
@@ -295,21 +328,26 @@ def main_gpu(args):
     bb = np.ascontiguousarray(b.reshape(-1))
     _lib.check(lib.b200l_set_problem(ctx, _lib.dptr(bb)))
 
-    def sweep():
-        _lib.check(lib.b200l_run(ctx, None, BLOCK, float(mu), -1.0, None, None, None, None, None))
+    # One launch of the persistent kernel per timed sweep (the unit the roofline and the committed
+    # ncu launch list refer to); --single-launch runs the K sweeps in one launch, like a solve.
+    def sweeps(n):
+        if not args.single_launch:
+            for _ in range(n):
+                _lib.check(lib.b200l_run(ctx, None, BLOCK, float(mu), -1.0, None, None, None, None, None))
+        elif n > 0:
+            _lib.check(lib.b200l_run(ctx, None, BLOCK * n, float(mu), -1.0, None, None, None, None, None))
 
-    for _ in range(args.warmup):
-        sweep()
-    barrier()
+    # (the sampler starts before the warm-up: its start-up must not delay rank 0 behind the others)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    sweeps(args.warmup)
+    barrier()
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     ev0.record()
-    for _ in range(args.steps):
-        sweep()
+    sweeps(args.steps)
     ev1.record()
     barrier()
     t_wall1 = time.time()
@@ -331,7 +369,9 @@ def main_gpu(args):
         _lib.check(lib.b200l_run(ctx, None, BLOCK, float(mu), -1.0, None, None, None, None,
                                  ctypes.byref(kms)))
         ktimes.append(kms.value)
-    kernel_ms = ms_per_step
+    sweeps_per_launch = args.steps if args.single_launch else 1
+    n_launches = args.steps // sweeps_per_launch
+    kernel_ms = ms / n_launches                  # average duration of the launches of the timed region
     kernel_ms_alone = float(np.mean(ktimes))
     obj = ctypes.c_double()
     _lib.check(lib.b200l_objective(ctx, float(mu), ctypes.byref(obj)))
@@ -373,16 +413,18 @@ def main_gpu(args):
     if rank == 0:
         W = sweep_bytes(N, K, BLOCK, s)
         peak, peak_src = measured_peak()
-        achieved = W / (kernel_ms * 1e-3) / 1e9
-        traffic = None if args.small else ncu_traffic(args.config, layout)
+        achieved = W * sweeps_per_launch / (kernel_ms * 1e-3) / 1e9
+        traffic_sweep = None if args.small else ncu_traffic(args.config, layout)
+        traffic = None if traffic_sweep is None else traffic_sweep * sweeps_per_launch
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32" if s == 4 else "f64",
             "data": "synthetic",
-            "config": {"workload": "dense %s lasso %dx%d, %d column blocks, %s A layout; 1 step = 1 sweep; "
+            "config": {"workload": "dense %s lasso %dx%d, %d column blocks, %s A layout; 1 step = 1 sweep, the timed "
+                                   "sweeps run in %d launch(es) of the persistent kernel; "
                                    "A=%.1f GB per GPU >> L2 so no flush between steps%s"
-                                   % ("fp32" if s == 4 else "fp64", N, K * world, BLOCK, layout,
+                                   % ("fp32" if s == 4 else "fp64", N, K * world, BLOCK, layout, n_launches,
                                       N * K * s / 1e9,
                                       ("; column-sharded over %d GPUs (slice g of every block on GPU g, partial "
                                        "A_m D summed in-kernel over NVLink peer memory); value counts C2-sized "
@@ -393,11 +435,13 @@ def main_gpu(args):
                          "frac": achieved / peak, "traffic": traffic,
                          "kernel": "lasso_fused<%s,1,%s>" % ("float" if s == 4 else "double",
                                                              "TRANS" if layout == "transposed" else "ROWMAJOR"),
-                         "kernel_ms_per_launch": kernel_ms,
-                         "kernel_ms_per_launch_alone": kernel_ms_alone,
-                         "algorithmic_bytes_per_launch": W, "peak_source": peak_src,
+                         "kernel_ms_per_launch": kernel_ms, "sweeps_per_launch": sweeps_per_launch,
+                         "ms_per_single_sweep_launch_alone": kernel_ms_alone,
+                         "algorithmic_bytes_per_launch": W * sweeps_per_launch,
+                         "algorithmic_bytes_per_sweep": W, "traffic_per_sweep": traffic_sweep,
+                         "peak_source": peak_src,
                          "frac_of_nominal_8TBs": achieved / 8000.0,
-                         "dram_single_pass_GBs": (W - N * K * s) / (kernel_ms * 1e-3) / 1e9,
+                         "dram_single_pass_GBs": (W - N * K * s) * sweeps_per_launch / (kernel_ms * 1e-3) / 1e9,
                          "note": "algorithmic bytes count A twice per sweep (SURVEY 8d); the second pass of a "
                                  "40 MB block is served by L2, so DRAM traffic is about half of it (see traffic)"},
             "e2e": {"value": e2e_value, "unit": UNIT,
@@ -405,7 +449,7 @@ def main_gpu(args):
                     "d2h_bytes_per_step": int(K * 8 + 24),
                     "sweeps_per_call": e2e_sweeps, "calls": e2e_steps, "nnz_x": nnz,
                     "api": "ClassLasso.run() (host b -> device, fused solve, x -> host)"},
-            "gpu_launches": args.steps,
+            "gpu_launches": n_launches,
             "clocks": clocks,
         }
         if tte:
@@ -429,6 +473,8 @@ def main():
     ap.add_argument("--small", action="store_true", help="2000x20000 debug size (not a bench value)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-sweeps", type=int, default=5)
+    ap.add_argument("--single-launch", action="store_true",
+                    help="run the K timed sweeps in one kernel launch instead of one launch per sweep")
     ap.add_argument("--eps", type=float, default=1e-4, help="ERR_BOUND of the time-to-eps leg (0 = skip)")
     ap.add_argument("--eps-max-sweeps", type=int, default=2000)
     ap.add_argument("--slot-bytes", type=int, default=0)

@@ -100,6 +100,8 @@ def main():
                "ms_per_sweep_traced": kms.value / args.sweeps, "ms_per_sweep": float(np.median(ts)),
                "sweeps_per_s": 1e3 / float(np.median(ts)),
                "us_per_block_step": float(step_len.mean()),
+               "us_per_block_step_by_sweep": [round(float(step_len[:, i * BLOCK:(i + 1) * BLOCK].mean()), 2)
+                                              for i in range(max(1, step_len.shape[1] // BLOCK))],
                "phases_us_mean_over_ctas": {n: round(float(dur[:, :, i].mean()), 3) for i, n in enumerate(PHASES)},
                "phases_us_max_cta": {n: round(float(dur[:, :, i].mean(axis=1).max()), 3) for i, n in enumerate(PHASES)},
                "phases_us_min_cta": {n: round(float(dur[:, :, i].mean(axis=1).min()), 3) for i, n in enumerate(PHASES)},
@@ -145,7 +147,7 @@ def main():
         if world > 1:
             out["rank"] = rank
         if rank == 0 or args.all_ranks:
-            print(json.dumps({k: out[k] for k in ("tuning", "ms_per_sweep", "sweeps_per_s", "us_per_block_step",
+            print(json.dumps({k: out[k] for k in ("tuning", "ms_per_sweep", "sweeps_per_s", "us_per_block_step", "us_per_block_step_by_sweep",
                                                    "phases_us_mean_over_ctas", "skew_us_pass1_end",
                                                    "gather_g_detail_us", "peer_rows_us", "tiles_us", "rank") if k in out}))
         sys.stdout.flush()
