@@ -68,7 +68,7 @@ def ncu_traffic(config, layout):
 # ------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region: NVML polled from a thread
-    every ~2 ms (nvidia_ml_py), nvidia-smi -lms as a fallback."""
+    every ~4 ms (nvidia_ml_py), nvidia-smi -lms as a fallback."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -115,7 +115,7 @@ class ClockSampler:
                 self.rows.append((time.time(), sm, self.max_mhz, [n for n, b in bits.items() if mask & b]))
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.004)
 
     def _pump(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -144,7 +144,7 @@ class ClockSampler:
         return {"sm_mhz": float(np.median([r[1] for r in rows])) if rows else None,
                 "sm_max_mhz": float(max(r[2] for r in rows)) if rows else None,
                 "reasons": reasons, "samples": len(inside),
-                "source": "nvml, 2 ms period" if self.nvml is not None else "nvidia-smi -lms 20"}
+                "source": "nvml, 4 ms period" if self.nvml is not None else "nvidia-smi -lms 20"}
 
 
 # ------------------------------------------------------------------------------ data

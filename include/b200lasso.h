@@ -122,8 +122,8 @@ int b200l_run(b200l_ctx *ctx, const int32_t *order_host, int64_t nsteps, double 
 /* launch geometry of the fused kernel for this context (for DESIGN/bench reporting) */
 int b200l_run_config(b200l_ctx *ctx, int32_t *grid, int32_t *threads, int32_t *smem_bytes,
                      int32_t *tile_rows, int32_t *ring_slots, int32_t *tiles_per_slab);
-/* tunables: ring slot bytes target (0 = default 64 KiB), bulk copies in flight per CTA
- * (0 = ring size) */
+/* tunables: ring slot bytes target (0 = default: 48 KiB when a block stays in L2 between the two
+ * passes, else 64 KiB), bulk copies in flight per CTA (0 = ring size) */
 int b200l_set_tuning(b200l_ctx *ctx, int32_t slot_bytes_target, int32_t max_inflight_tiles);
 
 /* Diagnostics of the hot path.  run_traced runs `nsteps` unbounded steps (cyclic order,
