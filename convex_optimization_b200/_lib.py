@@ -84,6 +84,9 @@ PROTOTYPES = {
                          ctypes.POINTER(ctypes.c_uint64), _pi32, _pd]),
     "b200l_set_wait_limit": (_c_int, [_p, _c_dbl]),
     "b200l_debug_flags": (_c_int, [_p, _c_i32]),
+    "b200l_gen_gaussian": (_c_int, [_p, ctypes.c_uint64, _c_i32, _c_i32]),
+    "b200l_row_sumsq": (_c_int, [_p, _pd]),
+    "b200l_scale_rows": (_c_int, [_p, _pd]),
     "b200l_comm_export": (_c_int, [_p, _c_i32, _c_i32, _p, _c_i32]),
     "b200l_comm_connect": (_c_int, [_p, _p, _c_i32]),
     "b200l_comm_destroy": (_c_int, [_p]),

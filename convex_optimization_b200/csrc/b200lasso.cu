@@ -1623,6 +1623,98 @@ __global__ void __launch_bounds__(1024) objective_kernel(const double *__restric
 // ------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------
+// synthetic instances on the device (parameters.py:20-28: A iid N(0,1), unit-l2 rows)
+// ------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  The entry (row i, GLOBAL column k) is a pure function of
+// (seed, i, k): counter = (k / 4, i, 0, "LASO"), key = seed; the four outputs make the normals of
+// columns 4*(k/4) .. +3 (Box-Muller on 24-bit uniforms).  Any column sharding therefore yields
+// the same matrix.
+__host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = 0xD2511F53ull * c0, p1 = 0xCD9E8D57ull * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ float gauss_entry(unsigned long long seed, uint32_t row, unsigned long long gcol) {
+    uint32_t x[4];
+    philox4x32_10((uint32_t)(gcol >> 2), row, (uint32_t)(gcol >> 34), 0x4c41534fu, (uint32_t)seed,
+                  (uint32_t)(seed >> 32), x);
+    const int e = (int)(gcol & 3);
+    const uint32_t a = (e & 2) ? x[2] : x[0], b = (e & 2) ? x[3] : x[1];
+    const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    return rad * ((e & 1) ? sn : cs);
+}
+// local column j of block m on rank `rank` of `world` is global column m*w*world + rank*w + j
+template <typename T, bool TRANS>
+__global__ void __launch_bounds__(256) gen_fill(T *A, int64_t N, int w, int nblocks, int64_t brows, int64_t ld,
+                                                unsigned long long seed, int rank, int world) {
+    const int64_t total = (int64_t)nblocks * N * w;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t i, j, m;
+        if (TRANS) { i = idx % N; j = (idx / N) % w; m = idx / (N * (int64_t)w); }
+        else       { j = idx % w; i = (idx / w) % N; m = idx / (N * (int64_t)w); }
+        const unsigned long long gcol = (unsigned long long)m * w * world + (unsigned long long)rank * w + j;
+        const float v = gauss_entry(seed, (uint32_t)i, gcol);
+        A[TRANS ? (m * brows + j) * ld + i : (m * brows + i) * ld + j] = (T)v;
+    }
+}
+// out[i] = sum over the local columns of A_ik^2 (one thread per row i; TRANS reads are coalesced,
+// row-major uses a warp per row)
+template <typename T, bool TRANS>
+__global__ void __launch_bounds__(256) row_sumsq(const T *A, int64_t N, int w, int nblocks, int64_t brows, int64_t ld,
+                                                 double *out) {
+    if (TRANS) {
+        const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= N) return;
+        double acc = 0.0;
+        for (int64_t mj = 0; mj < (int64_t)nblocks * w; ++mj) {
+            const int64_t m = mj / w, j = mj % w;
+            const double v = (double)A[(m * brows + j) * ld + i];
+            acc += v * v;
+        }
+        out[i] = acc;
+    } else {
+        const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        const int lane = threadIdx.x & 31;
+        if (i >= N) return;
+        double acc = 0.0;
+        for (int m = 0; m < nblocks; ++m) {
+            const T *row = A + ((int64_t)m * brows + i) * ld;
+            for (int j = lane; j < w; j += 32) {
+                const double v = (double)row[j];
+                acc += v * v;
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) out[i] = acc;
+    }
+}
+template <typename T, bool TRANS>
+__global__ void __launch_bounds__(256) scale_rows(T *A, int64_t N, int w, int nblocks, int64_t brows, int64_t ld,
+                                                  const double *scale) {
+    const int64_t total = (int64_t)nblocks * N * w;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t i, j, m;
+        if (TRANS) { i = idx % N; j = (idx / N) % w; m = idx / (N * (int64_t)w); }
+        else       { j = idx % w; i = (idx / w) % N; m = idx / (N * (int64_t)w); }
+        T *e = A + (TRANS ? (m * brows + j) * ld + i : (m * brows + i) * ld + j);
+        *e = (T)((double)*e * scale[i]);
+    }
+}
+
 struct b200l_ctx {
     int dtype, layout, device;
     int64_t N, K;
@@ -1927,6 +2019,64 @@ extern "C" int b200l_gemv_n(b200l_ctx *c, int32_t m, const double *d_host, doubl
                                    : gemv_n_dev<double>(c, m, c->vin, c->vout, 0);
     if (rc) return rc;
     CK(cudaMemcpyAsync(q_host, c->vout, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// synthetic instance generation (reference recipe parameters.py:20-28)
+// ------------------------------------------------------------------------------------
+template <typename T>
+static int gen_dispatch(b200l_ctx *c, int what, unsigned long long seed, int rank, int world, const double *scale,
+                        double *out) {
+    T *A = reinterpret_cast<T *>(const_cast<void *>(c->A));
+    const bool trans = c->layout == B200L_TRANSPOSED;
+    const int64_t total = (int64_t)c->nblocks * c->N * c->w;
+    const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)c->sm_count * 32);
+    if (what == 0) {
+        if (trans) gen_fill<T, true><<<grid, 256, 0, c->stream>>>(A, c->N, c->w, c->nblocks, c->brows, c->ld, seed, rank, world);
+        else gen_fill<T, false><<<grid, 256, 0, c->stream>>>(A, c->N, c->w, c->nblocks, c->brows, c->ld, seed, rank, world);
+    } else if (what == 1) {
+        if (trans) row_sumsq<T, true><<<(int)((c->N + 255) / 256), 256, 0, c->stream>>>(A, c->N, c->w, c->nblocks, c->brows, c->ld, out);
+        else row_sumsq<T, false><<<(int)((c->N * 32 + 255) / 256), 256, 0, c->stream>>>(A, c->N, c->w, c->nblocks, c->brows, c->ld, out);
+    } else {
+        if (trans) scale_rows<T, true><<<grid, 256, 0, c->stream>>>(A, c->N, c->w, c->nblocks, c->brows, c->ld, scale);
+        else scale_rows<T, false><<<grid, 256, 0, c->stream>>>(A, c->N, c->w, c->nblocks, c->brows, c->ld, scale);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200l_gen_gaussian(b200l_ctx *c, uint64_t seed, int32_t rank, int32_t world) {
+    if (need_A(c)) return 1;
+    if (world < 1 || rank < 0 || rank >= world) return fail("bad rank %d / world %d", rank, world);
+    const int rc = c->dtype == B200L_F32 ? gen_dispatch<float>(c, 0, seed, rank, world, nullptr, nullptr)
+                                         : gen_dispatch<double>(c, 0, seed, rank, world, nullptr, nullptr);
+    if (rc) return rc;
+    c->have_problem = 0;
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int b200l_row_sumsq(b200l_ctx *c, double *out_host) {
+    if (need_A(c)) return 1;
+    if (!out_host) return fail("out_host is NULL");
+    const int rc = c->dtype == B200L_F32 ? gen_dispatch<float>(c, 1, 0, 0, 1, nullptr, c->vout)
+                                         : gen_dispatch<double>(c, 1, 0, 0, 1, nullptr, c->vout);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_host, c->vout, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int b200l_scale_rows(b200l_ctx *c, const double *scale_host) {
+    if (need_A(c)) return 1;
+    if (!scale_host) return fail("scale_host is NULL");
+    CK(cudaMemcpyAsync(c->vin, scale_host, (size_t)c->N * 8, cudaMemcpyHostToDevice, c->stream));
+    const int rc = c->dtype == B200L_F32 ? gen_dispatch<float>(c, 2, 0, 0, 1, c->vin, nullptr)
+                                         : gen_dispatch<double>(c, 2, 0, 0, 1, c->vin, nullptr);
+    if (rc) return rc;
+    c->have_problem = 0;
     CK(cudaStreamSynchronize(c->stream));
     return 0;
 }

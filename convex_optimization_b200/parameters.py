@@ -55,3 +55,80 @@ def parameters(N, K, den, SAVE_FLAG, READ_FLAG, SILENCE=False, seed=None):
         if not SILENCE:
             print("Paramenters @@saved!")
     return (A, x_true, b, mu)
+
+
+def parameters_device(N, K, BLOCK, den, seed, gpu_cal_cls=None, group=None, SILENCE=True):
+    """The recipe of ``parameters()`` (parameters.py:20-33) for instances that never exist on the
+    host: ``A`` is generated on the device by ``b200l_gen_gaussian``
+    (counter-based Philox keyed by (seed, row, global column), so every column sharding yields
+    the same matrix), rows are scaled to unit l2 norm, ``b = A x_true + e`` and
+    ``mu = 0.1 |A^T b|_inf`` come from the library's mat-vecs.  ``K`` is the GLOBAL column count;
+    with an initialised ``torch.distributed`` group every rank builds its column slice of every
+    block (``distributed.local_columns``) and the row norms, ``b`` and ``mu`` are all-reduced.
+    ``x_true`` and the noise are drawn on the host from ``RandomState(seed + 1)`` (identical on
+    all ranks; not the reference's ``sparse.random`` stream).
+    Returns ``(gpu_cal, x_true (K,1), b (N,1), mu)``."""
+    import torch
+    from . import _lib
+    from .gpu_calculation import GPU_Calculation
+    cls = gpu_cal_cls or GPU_Calculation
+    dist = None
+    rank, world = 0, 1
+    try:
+        import torch.distributed as tdist
+        if tdist.is_available() and tdist.is_initialized():
+            dist = tdist
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+    except Exception:
+        dist = None
+    if K % (BLOCK * world):
+        raise ValueError("K=%d is not divisible by BLOCK*world=%d" % (K, BLOCK * world))
+    Kl = K // world
+    wl = Kl // BLOCK
+    device = torch.device("cuda", cls.DEVICE)
+    tdt = torch.float64 if cls.TYPE == 'double' else torch.float32
+    ld = cls.padded_ld(N, Kl, BLOCK)
+    rows = N if cls.LAYOUT == 'row' else wl
+    store = torch.zeros((BLOCK, rows, ld), dtype=tdt, device=device)
+    cal = cls.from_device_blocks(store, N, Kl, BLOCK)
+    lib, ctx = cal._lib, cal.ctx
+
+    def allreduce(a, op):
+        if dist is None:
+            return a
+        t = torch.from_numpy(a)
+        if dist.get_backend(group) == "nccl":
+            t = t.to(device)
+        dist.all_reduce(t, op=op, group=group)
+        return t.cpu().numpy()
+
+    _lib.check(lib.b200l_gen_gaussian(ctx, int(seed) & 0xFFFFFFFFFFFFFFFF, rank, world))
+    ss = np.empty(N)
+    _lib.check(lib.b200l_row_sumsq(ctx, _lib.dptr(ss)))
+    ss = allreduce(ss, None if dist is None else dist.ReduceOp.SUM)
+    scale = np.ascontiguousarray(1.0 / np.sqrt(ss))
+    _lib.check(lib.b200l_scale_rows(ctx, _lib.dptr(scale)))
+
+    rs = np.random.RandomState(int(seed) + 1)
+    mask = rs.rand(K) < den
+    x_true = (rs.randn(K) * mask)[:, np.newaxis]
+    noise = rs.normal(0, np.sqrt(1e-4), N)
+    w = K // BLOCK                                       # global block width
+    b = np.zeros(N)
+    q = np.empty(N)
+    for m in range(BLOCK):
+        xm = np.ascontiguousarray(x_true[m * w + rank * wl:m * w + (rank + 1) * wl, 0])
+        _lib.check(lib.b200l_gemv_n(ctx, m, _lib.dptr(xm), _lib.dptr(q)))
+        b += q
+    b = allreduce(b, None if dist is None else dist.ReduceOp.SUM) + noise
+    b = np.ascontiguousarray(b)
+    g = np.empty(wl)
+    gmax = np.zeros(1)
+    for m in range(BLOCK):
+        _lib.check(lib.b200l_gemv_t(ctx, m, _lib.dptr(b), _lib.dptr(g)))
+        gmax[0] = max(gmax[0], float(np.max(np.abs(g))))
+    gmax = allreduce(gmax, None if dist is None else dist.ReduceOp.MAX)
+    mu = 0.1 * float(gmax[0])
+    if not SILENCE and rank == 0:
+        print("Parameters @@created on the device with N: %d, K: %d, DENSITY: %f, mu: %f." % (N, K, den, mu))
+    return cal, x_true, b[:, np.newaxis], mu

@@ -151,6 +151,18 @@ int b200l_set_wait_limit(b200l_ctx *ctx, double seconds);
  * pass-2 arithmetic of the fused kernel, to time the remaining parts.  Results are invalid. */
 int b200l_debug_flags(b200l_ctx *ctx, int32_t flags);
 
+/* -- synthetic instances on the device (reference recipe: parameters.py:20-28) ---------
+ * gen_gaussian fills the bound A with iid N(0,1) entries that are a pure function of
+ * (seed, row, GLOBAL column): Philox4x32-10, counter (column/4, row, 0, "LASO"), key = seed,
+ * Box-Muller on 24-bit uniforms.  rank/world say which column slice of every block this
+ * context holds (local column j of block m = global column m*w*world + rank*w + j), so any
+ * sharding yields the same matrix.  row_sumsq returns sum_k A_ik^2 over the LOCAL columns
+ * (N doubles; sum over the ranks, then scale_rows with 1/sqrt makes unit-l2 rows, parameters.py:22-23).
+ * No counterpart in the reference beyond the NumPy recipe. */
+int b200l_gen_gaussian(b200l_ctx *ctx, uint64_t seed, int32_t rank, int32_t world);
+int b200l_row_sumsq(b200l_ctx *ctx, double *out_host);
+int b200l_scale_rows(b200l_ctx *ctx, const double *scale_host);
+
 /* -- multi-GPU: one process per GPU ------------------------------------------------
  * Rank `rank` of `world` creates its context with the LOCAL column count (K/world): column
  * slice `rank` of every block, exactly the reference's P-way split of a block

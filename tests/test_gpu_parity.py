@@ -388,3 +388,83 @@ def test_full_size_c2_properties_fp32_vs_fp64():
     assert abs(o32[-1] - o64[-1]) / o64[-1] < TOL["float"]
     assert rel(r32, r64) < 1e-4
     assert 0 < np.count_nonzero(x64) < K // 10            # a sparse solution
+
+
+def _device_blocks(cal):
+    """(BLOCK, N, w) float64 copy of the device matrix, whatever the layout"""
+    t = cal._A_store.cpu().numpy().astype(np.float64)
+    if cal.LAYOUT == "row":
+        return t[:, :, :cal.MAT_WIDTH]
+    return np.transpose(t[:, :, :cal.MAT_HEIGHT], (0, 2, 1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("TYPE", ["float", "double"])
+@pytest.mark.parametrize("LAYOUT", ["row", "transposed"])
+def test_device_generator_matches_restatement_and_any_sharding(TYPE, LAYOUT):
+    """b200l_gen_gaussian: entries = f(seed, row, global column); checked against the NumPy
+    restatement (published Philox KATs in test_oracle) and across column shardings"""
+    import torch
+    from oracle import philox
+    from convex_optimization_b200 import _lib
+    from convex_optimization_b200.gpu_calculation import GPU_Calculation
+    N, K, BLOCK, seed = 203, 1200, 3, 0x1234567890ABCDEF
+    w = K // BLOCK
+
+    def fill(rank, world):
+        class Cal(GPU_Calculation):
+            pass
+        Cal.TYPE, Cal.LAYOUT = TYPE, LAYOUT
+        Kl = K // world
+        ld = Cal.padded_ld(N, Kl, BLOCK)
+        rows = N if LAYOUT == "row" else Kl // BLOCK
+        store = torch.zeros((BLOCK, rows, ld), dtype=torch.float32 if TYPE == "float" else torch.float64, device="cuda")
+        cal = Cal.from_device_blocks(store, N, Kl, BLOCK)
+        _lib.check(cal._lib.b200l_gen_gaussian(cal.ctx, seed, rank, world))
+        return cal, _device_blocks(cal)
+
+    cal, full = fill(0, 1)
+    want = philox.gauss_matrix(seed, N, np.arange(K)).astype(np.float64).reshape(N, BLOCK, w).transpose(1, 0, 2)
+    assert np.abs(full - want).max() < 2e-5          # logf / sincospif on the device vs NumPy
+    for world in (2, 4):
+        wl = w // world
+        for rank in range(world):
+            _, part = fill(rank, world)
+            assert np.array_equal(part, full[:, :, rank * wl:(rank + 1) * wl])
+    # row norms and scaling (parameters.py:22-23)
+    ss = np.empty(N)
+    _lib.check(cal._lib.b200l_row_sumsq(cal.ctx, _lib.dptr(ss)))
+    assert np.allclose(ss, (full ** 2).sum(axis=(0, 2)), rtol=1e-12)
+    scale = np.ascontiguousarray(1.0 / np.sqrt(ss))
+    _lib.check(cal._lib.b200l_scale_rows(cal.ctx, _lib.dptr(scale)))
+    scaled = _device_blocks(cal)
+    tol = 1e-6 if TYPE == "float" else 1e-14
+    assert np.allclose((scaled ** 2).sum(axis=(0, 2)), 1.0, atol=10 * tol)
+    # padding stays zero
+    assert float(cal._A_store.cpu().numpy().astype(np.float64).__abs__().sum()) == pytest.approx(np.abs(scaled).sum(), rel=1e-12)
+
+
+@pytest.mark.gpu
+def test_parameters_device_instance_solves_like_the_oracle():
+    """parameters_device(): unit rows, b, mu as in parameters.py:20-33, and the instance solved by the
+    fused kernel matches the oracle run on the downloaded matrix"""
+    from convex_optimization_b200 import lasso, parameters
+    from convex_optimization_b200.gpu_calculation import GPU_Calculation
+
+    class Cal(GPU_Calculation):
+        pass
+    Cal.TYPE, Cal.LAYOUT = "double", "row"
+    N, K, BLOCK = 300, 1800, 3
+    cal, x_true, b, mu = parameters.parameters_device(N, K, BLOCK, 0.05, 11, gpu_cal_cls=Cal)
+    blocks = _device_blocks(cal)
+    A = np.concatenate([blocks[m] for m in range(BLOCK)], axis=1)
+    assert np.allclose(np.linalg.norm(A, axis=1), 1.0, atol=1e-12)
+    assert mu == pytest.approx(0.1 * np.max(np.abs(A.T @ b)), rel=1e-12)
+    assert np.linalg.norm(b[:, 0] - (A @ x_true)[:, 0]) < 0.05 * np.sqrt(N)      # noise sd 1e-2
+    ITER_MAX = 300 * BLOCK
+    o = orc.lasso_oracle(A, b, mu, BLOCK, ITER_MAX, 1e-4, faithful=False)
+    s = lasso.ClassLasso(cal, cal.diag_ATA, A, b, mu, BLOCK, ITER_MAX)
+    s.run(1e-4, SILENCE=True)
+    assert s.iters == o["iters"]
+    assert np.array_equal(s.x != 0, o["x"] != 0)
+    assert rel(s.x, o["x"]) < 1e-10

@@ -72,3 +72,20 @@ def test_sweep_bytes_formula():
     # config 2 -> 8.00 GB + 0.02 GB
     W = orc.sweep_bytes(10000, 100000, 100, 4)
     assert W == 2 * 10000 * 100000 * 4 + 5 * 100 * 10000 * 4 + 4 * 100000 * 4
+
+
+def test_philox_restatement_matches_published_known_answers():
+    """Random123 kat_vectors for philox4x32-10: the restatement used to check b200l_gen_gaussian"""
+    from oracle import philox
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+             (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kats:
+        got = philox.philox4x32_10(*ctr, *key)
+        assert tuple(int(v) for v in got) == want
+    g = philox.gauss_matrix(7, 500, np.arange(400)).astype(np.float64)
+    assert abs(g.mean()) < 0.01 and abs(g.std() - 1.0) < 0.01
+    # a pure function of (seed, row, global column): any column subset gives the same entries
+    cols = np.array([3, 17, 64, 399])
+    assert np.array_equal(philox.gauss_matrix(7, 500, cols), philox.gauss_matrix(7, 500, np.arange(400))[:, cols])
