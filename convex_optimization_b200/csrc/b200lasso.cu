@@ -325,8 +325,8 @@ struct RunParams {
     int32_t TR, S, slot_bytes, cs, cs_shift, nrg, ncg, rows_pad, rows_max_, inflight, l2_ahead, l2_pass;
     // multi-GPU: rank `rank` of `world` holds column slice `rank` of every block; peer[r] is the
     // q-inbox of rank r: [2 parities][G CTAs][world sources][qw] words (peer[rank] is local)
-    int32_t xmode;            // cross-rank exchange: 0 per-tile sends + bulk-copy gather, 1 per-row sends + polled gather
-    int32_t world, rank, qw, qx_words;   // qx_words != 0: the collector warp sends the partial rows tile by tile
+    int32_t xmode;            // multi-GPU send side: 0 the sender warp sends finished pass-2 tiles, 1 the lane that finishes a row sends it
+    int32_t world, rank, qw, tile_sends; // qw: words per rank in a cell; tile_sends: plan for xmode 0
     ulonglong2 *peer[B200L_MAX_WORLD];
     int32_t direct_pub;       // partial gradients are published from registers (one row group)
     int32_t gate_mode;        // 0: re-stream freely, 1/2/3: after inbox fetch issued / gather done / D fetch issued
@@ -336,7 +336,7 @@ struct RunParams {
     int32_t mw, gc, dchunk, nown;   // message words, sources per gather group, D words per fetch, owner CTAs
     // shared-memory offsets
     int32_t off_bar, off_ctl, off_rloc, off_qloc, off_rT, off_qT, off_delta, off_redT, off_colsum,
-        off_small, off_qpart, off_qx, off_tilecnt, ring_bytes;
+        off_small, off_qpart, off_tilecnt, ring_bytes;
 };
 
 // bounded spinning: returns false when the wait has to be abandoned (a peer timed out or
@@ -1329,7 +1329,7 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                 }
             };
             if (WORLD > 1 && tid == 0) {   // my l1 / err terms of this step travel with the rows
-                if (p.xmode == 1) {        // (otherwise the collector warp sends them)
+                if (p.xmode == 1) {        // (otherwise the sender warp sends them)
                     send_row(rows_c, ctl->sp[2]);
                     send_row(rows_c + 1, ctl->sp[3]);
                 }
@@ -1410,7 +1410,7 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                             }
                         }
                         if (WORLD > 1 && p.xmode == 0) {
-                            // multi-GPU: count the warps that are done with this tile; the collector
+                            // multi-GPU: count the warps that are done with this tile; the sender
                             // warp sends the tile's rows to the peers when all are
                             __syncwarp();
                             if (lane == 0) {
@@ -2297,18 +2297,17 @@ static int plan_geometry(b200l_ctx *c) {
         const int o_colsum = take(2 * (4 + MAX_CS) * 16);         // gathered scalars + columns (+ group sums)
         const int o_small = take((2 * MAX_CS + 2 * NW) * 8);      // l1s, es, lsred
         const int o_qpart = take(rows_pad * 8);
-        const int o_qx = take(16);
         const int o_tilecnt = take(128 * 4);
         if (out) {
             out->off_bar = o_bar; out->off_ctl = o_ctl; out->off_rloc = o_rloc; out->off_qloc = o_qloc;
             out->off_rT = o_rT; out->off_qT = o_qT; out->off_delta = o_delta; out->off_redT = o_redT;
             out->off_colsum = o_colsum; out->off_small = o_small; out->off_qpart = o_qpart;
-            out->off_qx = o_qx; out->off_red2 = o_red2; out->off_tilecnt = o_tilecnt;
-            // multi-GPU send side: the collector warp sends the rows of a pass-2 tile when the
+            out->off_red2 = o_red2; out->off_tilecnt = o_tilecnt;
+            // multi-GPU send side: the sender warp sends the rows of a pass-2 tile when the
             // consumer warps are done with it (row-major, up to 128 tiles); otherwise the lane that
             // finishes a row stores it to every peer itself (also forced by dbg bit 8)
             const int nt_plan = trans ? nt_t : (rows_max + TR - 1) / TR;
-            out->qx_words = (c->world > 1 && !trans && nt_plan <= 128 && !(c->dbg & 256)) ? 1 : 0;
+            out->tile_sends = (c->world > 1 && !trans && nt_plan <= 128 && !(c->dbg & 256)) ? 1 : 0;
         }
     };
     // the ring goes first (offset 0); sized after the fixed part is known
@@ -2466,8 +2465,8 @@ static int launch_fused(b200l_ctx *c, const int32_t *order_host, int64_t nsteps,
     p.world = c->world;
     p.rank = c->rank;
     p.qw = c->world > 1 ? (int32_t)round_up(c->geo.rows_max_ + 2, 2) : 0;
-    p.qx_words = c->geo.qx_words;
-    p.xmode = c->geo.qx_words ? 0 : 1;
+    p.tile_sends = c->geo.tile_sends;
+    p.xmode = c->geo.tile_sends ? 0 : 1;
     for (int r = 0; r < B200L_MAX_WORLD; ++r) p.peer[r] = c->peer[r];
     p.dbg = c->dbg;
 
