@@ -745,11 +745,14 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                     }
                     for (;;) {
                         if (own_rows < rows_c) {
-                            // final rows of my own partial product: all of them once pass 2 is
-                            // complete, else what the sender warp has sent
+                            // final rows of my own partial product: what the sender warp has sent (so
+                            // the consumers, who wait for this warp, can never overwrite rows the sender
+                            // still has to read), or all of them once pass 2 is complete when the
+                            // consumers send their rows themselves
                             const long long pd = *(volatile long long *)&ctl->p2done;
                             const long long orw = *(volatile long long *)&ctl->own_rows;
-                            int mine_n = pd > hs ? rows_c : ((orw >> 32) == hs + 1 ? (int)(orw & 0x7fffffff) : 0);
+                            int mine_n = p.xmode == 0 ? ((orw >> 32) == hs + 1 ? (int)(orw & 0x7fffffff) : 0)
+                                                      : (pd > hs ? rows_c : 0);
                             mine_n = __reduce_min_sync(0xffffffffu, mine_n);
                             if (mine_n > own_rows) {
                                 own_rows = mine_n;
