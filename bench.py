@@ -267,6 +267,35 @@ def main_reference(args):
     return 0
 
 
+def c1_time_to_eps(device_index):
+    """BASELINE.json configs[0]: the reference's default instance (cpu_vs_gpu.py:57-74: N=1024, K=4096,
+    BLOCK=2, den=0.4, fp64, ERR_BOUND=1e-4, seed 1234) solved through ClassLasso.run() from host
+    arrays; reported beside the 52.45 s the unmodified ClassLassoCPU took in the survey
+    (BASELINE.md section 2).  Never fatal for the bench line."""
+    try:
+        from convex_optimization_b200 import lasso, parameters
+        from convex_optimization_b200.gpu_calculation import GPU_Calculation
+
+        class Cal(GPU_Calculation):
+            TYPE = "double"
+            LAYOUT = "row"
+            DEVICE = device_index
+        A, _, b, mu = parameters.parameters(1024, 4096, 0.4, False, False, SILENCE=True, seed=1234)
+        cal = Cal(A, 2)
+        solver = lasso.ClassLasso(cal, cal.diag_ATA, A, b, mu, 2, 1000)
+        solver.run(1e-4, SILENCE=True)                      # warm-up (module load, first launch)
+        t0 = time.time()
+        solver.run(1e-4, SILENCE=True)
+        dt = time.time() - t0
+        return {"workload": "default instance 1024x4096, BLOCK=2, fp64, ERR_BOUND=1e-4 (cpu_vs_gpu.py:57-74)",
+                "seconds": dt, "iterations": int(solver.iters), "nnz_x": int(np.count_nonzero(solver.x)),
+                "api": "ClassLasso.run() (host b in, x out)",
+                "reference_cpu_seconds_survey": 52.45, "reference_iterations_survey": 128}
+    except Exception as e:                                  # pragma: no cover
+        sys.stderr.write("c1_time_to_eps skipped: %r\n" % (e,))
+        return None
+
+
 # ------------------------------------------------------------------------------ GPU arm
 def main_gpu(args):
     import torch
@@ -454,6 +483,10 @@ def main_gpu(args):
         }
         if tte:
             line["time_to_eps"] = tte
+        if world == 1 and not args.small and args.eps > 0:
+            c1 = c1_time_to_eps(local_rank)
+            if c1:
+                line["c1_time_to_eps"] = c1
         if not args.no_cpu and world == 1:
             line["cpu_baseline"] = cpu_baseline_block()
         print(json.dumps(line))
