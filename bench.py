@@ -331,9 +331,14 @@ def main_gpu(args):
     tdt = torch.float32 if cfg["dtype"] == "float" else torch.float64
     # N GPUs: the instance grows with N (weak scaling): K = 100000*N columns, 100 blocks of width
     # 1000*N, column slice `rank` of every block per GPU, i.e. one C2-sized shard per GPU
-    store, b, mu = make_device_instance(torch, device, N, K, BLOCK, cfg["den"], cfg["seed"], tdt, ld, layout,
-                                        dist if world > 1 else None, rank)
-    cal = Cal.from_device_blocks(store, N, K, BLOCK)
+    if args.instance == "philox":
+        # the library's generator: the same global matrix for every world size
+        from convex_optimization_b200 import parameters as pm
+        cal, _, b, mu = pm.parameters_device(N, K * world, BLOCK, cfg["den"], cfg["seed"], gpu_cal_cls=Cal)
+    else:
+        store, b, mu = make_device_instance(torch, device, N, K, BLOCK, cfg["den"], cfg["seed"], tdt, ld, layout,
+                                            dist if world > 1 else None, rank)
+        cal = Cal.from_device_blocks(store, N, K, BLOCK)
     if world > 1:
         from convex_optimization_b200 import distributed as dd
         dd.connect(cal)
@@ -506,6 +511,9 @@ def main():
     ap.add_argument("--small", action="store_true", help="2000x20000 debug size (not a bench value)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-sweeps", type=int, default=5)
+    ap.add_argument("--instance", default="torch", choices=["torch", "philox"],
+                    help="how the synthetic instance is generated on the device: torch RNG per rank (default) or "
+                         "b200l_gen_gaussian (Philox keyed by seed/row/global column)")
     ap.add_argument("--single-launch", action="store_true",
                     help="run the K timed sweeps in one kernel launch instead of one launch per sweep")
     ap.add_argument("--eps", type=float, default=1e-4, help="ERR_BOUND of the time-to-eps leg (0 = skip)")
