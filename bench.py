@@ -319,6 +319,11 @@ def main_gpu(args):
         cfg.update(N=20000, K=200000, BLOCK=100, dtype="double", seed=3)
     elif args.config == "c4shard":  # one GPU's share of configs[3] on 8 GPUs: 50,000 x 125,000 fp32 (25 GB)
         cfg.update(N=50000, K=125000, BLOCK=100, dtype="float", seed=4)
+    if args.shape:              # diagnostics only: N,K,BLOCK[,dtype]
+        f = args.shape.split(",")
+        cfg.update(N=int(f[0]), K=int(f[1]), BLOCK=int(f[2]))
+        if len(f) > 3:
+            cfg["dtype"] = f[3]
     N, K, BLOCK = cfg["N"], cfg["K"], cfg["BLOCK"]
     s = 4 if cfg["dtype"] == "float" else 8
     layout = args.layout
@@ -521,6 +526,7 @@ def main():
     ap.add_argument("--slot-bytes", type=int, default=0)
     ap.add_argument("--inflight", type=int, default=0)
     ap.add_argument("--dbg", type=int, default=0, help="diagnostic flags of b200l_debug_flags (not for bench values)")
+    ap.add_argument("--shape", default="", help="diagnostics: N,K,BLOCK[,float|double] instead of a named config")
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4shard"],
                     help="c2 is the bench workload; the others are reported in DESIGN.md only")
     args = ap.parse_args()

@@ -91,6 +91,13 @@ PROTOTYPES = {
     "b200l_comm_connect": (_c_int, [_p, _p, _c_i32]),
     "b200l_comm_destroy": (_c_int, [_p]),
     "b200l_objective": (_c_int, [_p, _c_dbl, _pd]),
+    "b200l_objective_terms": (_c_int, [_p, _pd, _pd]),
+    "b200l_gemv_t_dev": (_c_int, [_p, _c_i32, _p, _p]),
+    "b200l_gemv_n_dev": (_c_int, [_p, _c_i32, _p, _p]),
+    "b200l_set_diag": (_c_int, [_p, _pd]),
+    "b200l_comm_close_peers": (_c_int, [_p]),
+    "b200l_comm_inbox_bytes": (_c_int, [_p, _c_i32, _pi64]),
+    "b200l_comm_attach": (_c_int, [_p, _c_i32, _c_i32, ctypes.POINTER(_p), _p]),
 }
 
 _lib = None

@@ -25,6 +25,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "b200lasso.h"
@@ -59,8 +60,13 @@ static int fail(const char *fmt, ...) {
 // ------------------------------------------------------------------------------------
 constexpr int NW = 8;                  // consumer warps
 constexpr int NTC = NW * 32;           // consumer threads
-constexpr int NTHREADS = NTC + 32;     // + one producer warp
-constexpr int NTHREADS_MG = NTC + 96;  // multi-GPU: + a warp that sends my partial rows and one that collects the peers'
+// + one helper warpgroup: warp 8 = TMA producer, multi-GPU: warp 9 sends my partial rows, warp 10
+// collects the peers'; warp 11 idles.  Twelve warps are launched with 168 registers each (what a
+// 384-thread CTA can have); the helper warpgroup then hands most of its share to the consumers
+// (setmaxnreg), whose inner loops want many loads in flight.
+constexpr int NTHREADS = NTC + 128;
+constexpr int HELPER_REGS = 56, CONSUMER_REGS = 224;            // 256 * 224 + 128 * 56 = 64512 = 384 * 168
+constexpr int HELPER_REGS_FULL = 96, CONSUMER_REGS_FULL = 200;  // (the collector warp keeps 14 words in flight)
 constexpr int MAX_CS = 64;             // max stage-2 slice width (columns per CTA)
 
 template <typename T> struct VT;
@@ -154,6 +160,10 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// phase / tile stamps of the traced runs: the SM's cycle counter (reading %globaltimer costs
+// ~0.2 us a time, which distorts a 12 us step; the trace carries a (globaltimer, clock) pair per
+// CTA at both ends of the launch to convert cycles to time)
+__device__ __forceinline__ unsigned long long tstamp() { return (unsigned long long)clock64(); }
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -195,19 +205,6 @@ __device__ __forceinline__ unsigned long long ll_ld1(const unsigned long long *p
 __device__ __forceinline__ void ll_st1(unsigned long long *p, unsigned long long a) {
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(a) : "memory");
 }
-// OR-reduction of a predicate over the consumer threads (named barrier 1)
-__device__ __forceinline__ bool cbar_or(bool pred) {
-    uint32_t out;
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\t"
-        "setp.ne.u32 q, %1, 0;\n\t"
-        "barrier.cta.red.or.pred p, 1, %2, q;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(out)
-        : "r"((uint32_t)pred), "n"(NTC)
-        : "memory");
-    return out != 0;
-}
 // two adjacent words with one 256-bit store (whole 32-byte sectors; p 32-byte aligned)
 __device__ __forceinline__ void ll_st2(ulonglong2 *p, unsigned long long a, unsigned long long b,
                                        unsigned long long c, unsigned long long d) {
@@ -239,10 +236,16 @@ template <> struct LLW<float> {
         a = (double)__uint_as_float((uint32_t)v[0].x);
         b = (double)__uint_as_float((uint32_t)v[0].y);
     }
-    __device__ static __forceinline__ void dput(ulonglong2 *base, int j, float v, uint32_t tag) {
-        ll_st(base + j, ll_pack(__float_as_uint(v), tag), ll_pack(0u, tag));
+    // the step D: one 16-byte word per column (dpw = 1: payload in the first half) or two columns
+    // per word (dpw = 2: one 8-byte half each)
+    __device__ static __forceinline__ void dwords(float v, uint32_t tag, unsigned long long &w0, unsigned long long &w1) {
+        w0 = ll_pack(__float_as_uint(v), tag);
+        w1 = ll_pack(0u, tag);
     }
-    __device__ static __forceinline__ float dval(const ulonglong2 v) { return __uint_as_float((uint32_t)v.x); }
+    __device__ static __forceinline__ void dget(const ulonglong2 v, int dpw, float *out) {
+        out[0] = __uint_as_float((uint32_t)v.x);
+        if (dpw == 2) out[1] = __uint_as_float((uint32_t)v.y);
+    }
     // the four columns of one column group: words p[0..3] = (g_r, g_q) pairs
     __device__ static __forceinline__ void put_group(ulonglong2 *p, const float4 r, const float4 q, uint32_t tag) {
         ll_st2(p, ll_pack(__float_as_uint(r.x), tag), ll_pack(__float_as_uint(q.x), tag),
@@ -254,17 +257,19 @@ template <> struct LLW<float> {
 template <> struct LLW<double> {
     static constexpr int WPC = 2;
     __device__ static __forceinline__ void put(ulonglong2 *p, double a, double b, uint32_t tag) {
-        ll_st_dbl(p, a, tag);
-        ll_st_dbl(p + 1, b, tag);
+        // one 32-byte sector, one store (p is an even word of a 256-byte aligned array)
+        ll_st2(p, ll_pack((uint32_t)__double2loint(a), tag), ll_pack((uint32_t)__double2hiint(a), tag),
+               ll_pack((uint32_t)__double2loint(b), tag), ll_pack((uint32_t)__double2hiint(b), tag));
     }
     __device__ static __forceinline__ void get(const ulonglong2 (&v)[2], double &a, double &b) {
         a = ll_dbl(v[0]);
         b = ll_dbl(v[1]);
     }
-    __device__ static __forceinline__ void dput(ulonglong2 *base, int j, double v, uint32_t tag) {
-        ll_st_dbl(base + j, v, tag);
+    __device__ static __forceinline__ void dwords(double v, uint32_t tag, unsigned long long &w0, unsigned long long &w1) {
+        w0 = ll_pack((uint32_t)__double2loint(v), tag);
+        w1 = ll_pack((uint32_t)__double2hiint(v), tag);
     }
-    __device__ static __forceinline__ double dval(const ulonglong2 v) { return ll_dbl(v); }
+    __device__ static __forceinline__ void dget(const ulonglong2 v, int, double *out) { out[0] = ll_dbl(v); }
     // the two columns of one column group: words p[0..3] = g_r, g_q, g_r, g_q
     __device__ static __forceinline__ void put_group(ulonglong2 *p, const double2 r, const double2 q, uint32_t tag) {
         ll_st2(p, ll_pack((uint32_t)__double2loint(r.x), tag), ll_pack((uint32_t)__double2hiint(r.x), tag),
@@ -276,8 +281,12 @@ template <> struct LLW<double> {
 
 constexpr int NTTRACE = 96;        // per-tile stamps: 6 groups of 16 (see b200lasso.h)
 constexpr int NTRACE = 16;         // time stamps per CTA and step of b200l_run_traced
-constexpr int NLD = 10;            // source CTAs per lane in the gather: grid <= 16 * NLD
-constexpr int GMAX = 16 * NLD;     // = 160
+#ifndef B200L_P1_UNROLL
+#define B200L_P1_UNROLL 1
+#endif
+constexpr int P1U = B200L_P1_UNROLL;   // row quads of pass 1 in flight per thread
+constexpr int NB = 8;              // exchange words a thread keeps in flight per round trip
+constexpr int GMAX = 160;          // largest grid (sizes the acknowledgement words of the step-D exchange)
 
 // ------------------------------------------------------------------------------------
 // fused kernel parameters
@@ -288,6 +297,8 @@ struct Ctl {
     int stop;
     int abort;
     long long gate;                  // steps whose pass-2 copies the producer may issue
+    long long sc_go, sc_done;        // steps whose scalars are final in sp / whose totals are in tot (scalar warp)
+    double tot[4];                   // line-search scalars of the pending step summed over all CTAs
     long long qready;                // multi-GPU: (step + 1) << 32 | rows of A_m D summed over the ranks
     long long p2start, p2done;       // multi-GPU: steps whose pass 2 (my partial rows) has begun / is complete
     long long own_rows;              // multi-GPU: (step + 1) << 32 | my rows that are final (and sent)
@@ -305,8 +316,9 @@ struct RunParams {
     const double *d;     // [nblocks][ld]
     const double *drec;  // [nblocks][ld]
     double *r;           // [N]
-    ulonglong2 *gLL;     // [G readers][G writers][mw]  scalars + partial block gradients
-    ulonglong2 *dLL;     // [ld]                        the step D
+    ulonglong2 *gLL;     // [G readers][G writers][mw]  partial block gradients
+    ulonglong2 *sLL;     // [G writers][4]              line-search scalars of the pending step
+    ulonglong2 *dLL;     // [ld + acks]                 the step D
     int *abort_flag;
     const int32_t *order;
     int64_t nsteps, step0;
@@ -322,7 +334,7 @@ struct RunParams {
     int32_t dbg;          // diagnostics only: 1 skip exchange waits, 2 skip pass-1 math, 4 skip pass-2 math
     unsigned long long wait_limit_ns;
     // geometry
-    int32_t TR, S, slot_bytes, cs, cs_shift, nrg, ncg, rows_pad, rows_max_, inflight, l2_ahead, l2_pass;
+    int32_t TR, S, slot_bytes, cs, cs_shift, nrg, ncg, rows_pad, rows_max_, inflight, l2_ahead;
     // multi-GPU: rank `rank` of `world` holds column slice `rank` of every block; peer[r] is the
     // q-inbox of rank r: [2 parities][G CTAs][world sources][qw] words (peer[rank] is local)
     int32_t xmode;            // multi-GPU send side: 0 the sender warp sends finished pass-2 tiles, 1 the lane that finishes a row sends it
@@ -333,9 +345,10 @@ struct RunParams {
     // transposed layout: a tile is TJ block columns x BX residual entries of this CTA
     // (BX/V odd: conflict-free 16-byte reads with lanes on consecutive columns)
     int32_t BX, BXV, TJ, nparts, nt_t, off_red2;
-    int32_t mw, gc, dchunk, nown;   // message words, sources per gather group, D words per fetch, owner CTAs
+    int32_t mw, mw_shift, nown;     // message words (a power of two), owner CTAs
+    int32_t dpw, dsec, ackbase;     // step D: columns per 16-byte word, published by whole sectors, first acknowledgement word
     // shared-memory offsets
-    int32_t off_bar, off_ctl, off_rloc, off_qloc, off_rT, off_qT, off_delta, off_redT, off_colsum,
+    int32_t off_bar, off_ctl, off_rloc, off_qloc, off_rT, off_qT, off_delta, off_redT, off_red,
         off_small, off_qpart, off_tilecnt, ring_bytes;
 };
 
@@ -372,34 +385,6 @@ struct Waiter {
         return true;
     }
 };
-
-// Exchange fetches land as one bulk copy; words that had not been written yet when the copy
-// read them are repaired one by one: thread `tid` owns the words tid + NTC*i of the landing
-// area (bit i of `mask` = still missing), re-reads them from L2, up to four in flight, until
-// their tags match, and patches the landing area.  No second bulk copy, no CTA-wide retry.
-__device__ __noinline__ void ll_repair(ulonglong2 *stage, const ulonglong2 *srcw, int tid, unsigned mask,
-                                       uint32_t tag, Waiter &waiter) {
-    while (mask) {
-        unsigned m = mask;
-        while (m) {
-            const int i0 = __ffs(m) - 1;
-            m &= m - 1;
-            const int i1 = m ? __ffs(m) - 1 : i0;
-            m &= m - 1;
-            const int i2 = m ? __ffs(m) - 1 : i0;
-            m &= m - 1;
-            const int i3 = m ? __ffs(m) - 1 : i0;
-            m &= m - 1;
-            const int e0 = tid + NTC * i0, e1 = tid + NTC * i1, e2 = tid + NTC * i2, e3 = tid + NTC * i3;
-            const ulonglong2 v0 = ll_ld(srcw + e0), v1 = ll_ld(srcw + e1), v2 = ll_ld(srcw + e2), v3 = ll_ld(srcw + e3);
-            if (ll_ok(v0, tag)) { stage[e0] = v0; mask &= ~(1u << i0); }
-            if (ll_ok(v1, tag)) { stage[e1] = v1; mask &= ~(1u << i1); }
-            if (ll_ok(v2, tag)) { stage[e2] = v2; mask &= ~(1u << i2); }
-            if (ll_ok(v3, tag)) { stage[e3] = v3; mask &= ~(1u << i3); }
-        }
-        if (mask && !waiter.again()) break;
-    }
-}
 
 // load 4 consecutive entries of a T vector in shared memory (16-byte aligned for float)
 __device__ __forceinline__ void load4(const float *p, float (&v)[4]) {
@@ -500,7 +485,7 @@ __device__ __forceinline__ T warp_sum_pair(const T a, const T b, const int lane)
 //       plain single-GPU solve runs the FULL = false instantiation: the per-step code has to
 //       stay resident in the instruction cache and every rarely used branch costs footprint.
 template <typename T, int CPT, bool TRANS, bool FULL>
-__global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(const RunParams p, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, const __grid_constant__ CUtensorMap tmap) {
     using VecT = typename VT<T>::type;
     using LL = LLW<T>;
     using OP = Ops<T>;
@@ -520,8 +505,7 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
     T *qT = reinterpret_cast<T *>(smem + p.off_qT);
     T *delta_s = reinterpret_cast<T *>(smem + p.off_delta);
     T *redT = reinterpret_cast<T *>(smem + p.off_redT);
-    double2 *colsum = reinterpret_cast<double2 *>(smem + p.off_colsum);   // [4 + cs]
-    uint64_t *xbar = full + 127;          // completion of the exchange fetches
+    double2 *red = reinterpret_cast<double2 *>(smem + p.off_red);         // [NTC] gather partials per thread
     double *l1s = reinterpret_cast<double *>(smem + p.off_small);
     double *es = l1s + MAX_CS;
     double *lsred = l1s + 2 * MAX_CS;     // [2][NW] line-search partials of the warps
@@ -551,11 +535,12 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
             mbar_init(full + s, 1);
             mbar_init(empty + s, NW);
         }
-        mbar_init(xbar, 1);
         ctl->sp[0] = ctl->sp[1] = ctl->sp[2] = ctl->sp[3] = 0.0;
         ctl->stop = 0;
         ctl->abort = 0;
         ctl->gate = 0;
+        ctl->sc_go = 0;
+        ctl->sc_done = 0;
         ctl->qready = 0;
         ctl->p2done = 0;
         ctl->p2start = 0;
@@ -570,6 +555,11 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
+    // register re-balancing between the warpgroups: every warp of a warpgroup executes it, first
+    // thing in its role branch (the allocator sizes each branch by the limit set inside it)
+    if (wid >= NW) {
+        if (FULL) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HELPER_REGS_FULL));
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HELPER_REGS));
     if (wid == NW) {
         // ============================ producer warp ================================
         if (lane == 0) {
@@ -594,9 +584,7 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                 }
                 const int ym = m * p.w, yn = (p.order ? (step + 1 < p.nsteps ? p.order[step + 1] : 0) : mc) * p.w;
                 for (int pass = 0; pass < 2 && live; ++pass) {
-                    // the re-stream for pass 2 is held back until the consumers have their
-                    // exchange fetch in flight: it would otherwise sit in front of it in the
-                    // TMA queue and on the L2 link
+                    // the re-stream for pass 2 can be held back (gate) behind the consumers' exchange
                     if (pass == 1 && p.gate_mode) {
                         while (*(volatile long long *)&ctl->gate <= step) {
                             if (*stopf) { live = false; break; }
@@ -624,18 +612,18 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                             mbar_expect_tx(full + cur.slot, (uint32_t)(p.TJ * p.BX) * (uint32_t)sizeof(T));
                             tma_load_2d(ring + (size_t)cur.slot * p.slot_bytes, &tmap, (int)row0, ym + t * p.TJ,
                                         full + cur.slot);
-                            if (pass == 1 - p.l2_pass && An) tma_prefetch_2d(&tmap, (int)row0, yn + t * p.TJ);
+                            if (pass == 1 && An) tma_prefetch_2d(&tmap, (int)row0, yn + t * p.TJ);
                         } else {
                             const uint32_t bytes = t == nt - 1 ? last_bytes : tile_bytes;
                             mbar_expect_tx(full + cur.slot, bytes);
                             tma_bulk_g2s(ring + (size_t)cur.slot * p.slot_bytes, Ab + (size_t)t * tile_bytes, bytes,
                                          full + cur.slot);
-                            // HBM runs one block ahead of the passes: while this step re-streams its
-                            // slab for pass 2 (L2 hits), pull the slab of the next step into L2
-                            if (pass == 1 - p.l2_pass && An) tma_prefetch_l2(An + (size_t)t * tile_bytes, bytes);
+                            // HBM runs one block ahead of the passes: while this step streams its slab
+                            // (from L2), pull the slab of the next step into L2
+                            if (pass == 1 && An) tma_prefetch_l2(An + (size_t)t * tile_bytes, bytes);
                         }
                         if (FULL && p.ttrace && t < 16)
-                            p.ttrace[((size_t)c * p.nsteps + step) * NTTRACE + 64 + pass * 16 + t] = globaltimer_ns();
+                            p.ttrace[((size_t)c * p.nsteps + step) * NTTRACE + 64 + pass * 16 + t] = tstamp();
                         cur.advance(S);
                         ++k;
                     }
@@ -822,14 +810,87 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                     ctl->sp[3] = ctl->qsc[1];
                     __threadfence_block();
                     *(volatile long long *)&ctl->qready = ((hs + 1) << 32) | 0x7fffffffLL;
+                    *(volatile long long *)&ctl->sc_go = hs + 1;         // the scalar warp takes them from here
                     if (p.trace)
                         p.trace[((size_t)c * p.nsteps + hs) * NTRACE + 15] =
-                            globaltimer_ns() - *(volatile unsigned long long *)&ctl->t_start;
+                            tstamp() - *(volatile unsigned long long *)&ctl->t_start;
                 }
             }
         }
-    } else if (wid < NW) {
+    } else if (wid == NW + 3) {
+        // ============== scalar warp: all-reduce of the line-search scalars ==============
+        // The four scalars of a step (r.q, q.q, the l1 difference, the error) are final when its
+        // pass 2 ends and are needed one pass later, when the NEXT step resolves gamma.  This warp
+        // runs their all-reduce in that window, off the consumers' critical path: publish my four
+        // words, fetch everybody's (lane = scalar lane % 4, writers lane / 4 + 8 i, SB in flight),
+        // add in writer order, combine the lanes with a fixed shuffle tree -> bitwise the same
+        // totals in every CTA, in ctl->tot.
+        {
+            constexpr int SB = 5;
+            Waiter hw{p.abort_flag, &ctl->abort, p.wait_limit_ns, 0u, 0ull, p.state + 4, 0};
+            volatile int *stopf = &ctl->stop;
+            const int ks = lane & 3;
+            bool live = true;
+            for (int64_t sidx = 0; sidx < p.nsteps && live; ++sidx) {
+                while (*(volatile long long *)&ctl->sc_go <= sidx) {
+                    if (*stopf || *(volatile int *)&ctl->abort) { live = false; break; }
+                    __nanosleep(64);
+                }
+                if (!live) break;
+                __threadfence_block();
+                const uint32_t tag = p.tag_base + (uint32_t)sidx + 2u;     // the tag of the step that consumes them
+                if (lane < 2) {                                            // two whole sectors
+                    const double s0 = *(volatile double *)&ctl->sp[2 * lane], s1 = *(volatile double *)&ctl->sp[2 * lane + 1];
+                    ll_st2(p.sLL + (size_t)c * 4 + 2 * lane,
+                           ll_pack((uint32_t)__double2loint(s0), tag), ll_pack((uint32_t)__double2hiint(s0), tag),
+                           ll_pack((uint32_t)__double2loint(s1), tag), ll_pack((uint32_t)__double2hiint(s1), tag));
+                }
+                hw.begin(((long long)sidx << 32) | (1LL << 30) | (long long)lane);
+                double acc = 0.0;
+#pragma unroll 1
+                for (int base = lane >> 2; base < G && live; base += 8 * SB) {
+                    ulonglong2 v[SB];
+                    unsigned miss = 0;
+#pragma unroll
+                    for (int i = 0; i < SB; ++i) {
+                        const int wr = base + 8 * i;
+                        if (wr < G) { v[i] = ll_ld(p.sLL + (size_t)wr * 4 + ks); miss |= 1u << i; }
+                    }
+                    const unsigned have = miss;
+#pragma unroll
+                    for (int i = 0; i < SB; ++i)
+                        if (((miss >> i) & 1u) && ll_ok(v[i], tag)) miss &= ~(1u << i);
+#pragma unroll 1
+                    while (miss && !(DBG & 1)) {
+                        if (*stopf || !hw.again()) { live = false; break; }
+#pragma unroll
+                        for (int i = 0; i < SB; ++i)
+                            if ((miss >> i) & 1u) v[i] = ll_ld(p.sLL + (size_t)(base + 8 * i) * 4 + ks);
+#pragma unroll
+                        for (int i = 0; i < SB; ++i)
+                            if (((miss >> i) & 1u) && ll_ok(v[i], tag)) miss &= ~(1u << i);
+                    }
+#pragma unroll
+                    for (int i = 0; i < SB; ++i)
+                        if ((have >> i) & 1u) acc = ks == 3 ? fmax(acc, ll_dbl(v[i])) : acc + ll_dbl(v[i]);
+                }
+                live = __all_sync(0xffffffffu, live);
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    const double ob = __shfl_xor_sync(0xffffffffu, acc, o);
+                    acc = ks == 3 ? fmax(acc, ob) : acc + ob;
+                }
+                if (lane < 4) ctl->tot[lane] = acc;
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) *(volatile long long *)&ctl->sc_done = sidx + 1;
+            }
+        }
+    }
+    } else {
         // ============================ consumer warps ===============================
+        if (FULL) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS_FULL));
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
         for (int i = tid; i < rows_c; i += NTC) {
             const double rv = p.r[row0 + i];
             r_loc[i] = rv;
@@ -847,7 +908,6 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
         bool have_prev = false;
         int m_prev = 0;
         int64_t step_prev = -1;
-        uint32_t xphase = 0;                                  // parity of the next exchange fetch
         double dprev = 0, xprev = 0;                          // column threads
         int64_t prev_idx = -1;
         long long block_cnt = p.state[2];
@@ -855,7 +915,8 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
         int stopped = 0, aborted = 0;
         int64_t steps_done = 0;
         const unsigned long long t_start = globaltimer_ns();
-        if (FULL && tid == 0) ctl->t_start = t_start;
+        const unsigned long long c_start = tstamp();
+        if (FULL && tid == 0) ctl->t_start = c_start;
         const int cs = p.cs, nrg = p.nrg;
         const double mu = p.mu;
         const uint32_t tag0 = p.tag_base;
@@ -904,15 +965,11 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
             const int m = drain ? 0 : (p.order ? p.order[step] : mc);
             if (++mc == p.nblocks) mc = 0;
             const uint32_t tag = tag0 + (uint32_t)step + 1u;
-            if (trace && !drain) trace[step * NTRACE + 0] = globaltimer_ns() - t_start;
+            if (trace && !drain) trace[step * NTRACE + 0] = tstamp() - c_start;
 
             // prox operands of my column: issued now, consumed after the gather
             const int64_t idx = (int64_t)m * ld + jcol;
             double xj = 0.0, dj = 0.0, drj = 0.0;
-            // the slot of the last pass-1 tile is held back as the landing area of the two
-            // exchange fetches and handed to the producer only before pass 2 (slot 0 is idle
-            // when this CTA has no rows or in the closing iteration)
-            int hold_slot = 0;
             if (!drain) {
                 if (has_col) {
                     dj = p.d[idx];
@@ -928,7 +985,7 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
 #pragma unroll 1
                 for (int t = 0; t < nt; ++t, ++kc) {
                     mbar_wait(full + cur.slot, cur.phase);
-                    if (ttrace && t < 16) ttrace[step * NTTRACE + t] = globaltimer_ns();
+                    if (ttrace && t < 16) ttrace[step * NTTRACE + t] = tstamp();
                     const T *tile = reinterpret_cast<const T *>(ring + (size_t)cur.slot * p.slot_bytes);
                     const int rows_t = min(TR, rows_c - t * TR);
                     const T *rTt = rT + t * TR, *qTt = qT + t * TR;
@@ -952,7 +1009,7 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                         if (j < G * cs) {
                             const int rd = j >> p.cs_shift;
                             const int jj = j & (cs - 1);
-                            LL::put(p.gLL + ((size_t)rd * G + c) * p.mw + 4 + jj * WPC, OP::hsum(a0), OP::hsum(a1), tag);
+                            LL::put(p.gLL + ((size_t)rd * G + c) * p.mw + jj * WPC, OP::hsum(a0), OP::hsum(a1), tag);
                         }
                     } else if (p1_active && !(DBG & 2)) {
                         if (TR >= 4) {
@@ -960,7 +1017,7 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                             // there is stale (possibly words of an exchange fetch, i.e. NaN bit
                             // patterns), so the last row of the tile is read in its place
                             const int nquad = (rows_t + 3) >> 2;
-#pragma unroll 1
+#pragma unroll(P1U)
                             for (int q4 = rg; q4 < nquad; q4 += nrg) {
                                 T rv[4], qv[4];
                                 load4(rTt + 4 * q4, rv);
@@ -1000,16 +1057,12 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                             }
                         }
                     }
-                    if (t == nt - 1) {
-                        hold_slot = cur.slot;
-                    } else {                        // hand the slot back to the producer
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(empty + cur.slot);
-                    }
-                    if (ttrace && t < 16) ttrace[step * NTTRACE + 16 + t] = globaltimer_ns();
+                    __syncwarp();                   // hand the slot back to the producer
+                    if (lane == 0) mbar_arrive(empty + cur.slot);
+                    if (ttrace && t < 16) ttrace[step * NTTRACE + 16 + t] = tstamp();
                     cur.advance(S);
                 }
-                if (trace) trace[step * NTRACE + 1] = globaltimer_ns() - t_start;
+                if (trace) trace[step * NTRACE + 1] = tstamp() - c_start;
 
                 // when every thread holds complete column sums (one row group) the partial
                 // gradient goes out straight from registers: the V columns of a column group
@@ -1025,7 +1078,7 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                                 const int j = cg * V;
                                 const int rd = j >> p.cs_shift;
                                 const int jj = j & (cs - 1);
-                                LL::put_group(p.gLL + ((size_t)rd * G + c) * p.mw + 4 + jj * WPC, OP::pack(ar[k]),
+                                LL::put_group(p.gLL + ((size_t)rd * G + c) * p.mw + jj * WPC, OP::pack(ar[k]),
                                               OP::pack(aq[k]), tag);
                             }
                         }
@@ -1042,12 +1095,16 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                     }
                 }
             }
-            if (WORLD > 1 && have_prev) wait_q(step_prev, 0x7fffffff);
+#ifdef B200L_PUBBAR
             cbar();
+#else
+            if (!p.direct_pub && !drain) cbar();       // the row-group partials in shared memory are complete
+#endif
             // ---------------- publish: one message of MW words per reader -------------------
-            // [0..3] my line-search scalars of the pending step, [4..] the partial gradient of
-            // the cs columns that reader owns (one column per thread: a warp stores whole
-            // 128-byte lines), then padding up to the message length
+            // the partial gradient (g_r, g_q) of the cs columns that reader owns: MW = cs * WPC
+            // words, a power of two (C2: 8 words = one 128-byte line per reader).  My four
+            // line-search scalars of the pending step go to a small array of their own: every CTA
+            // needs all of them, so they are written once instead of once per reader.
             {
                 const int MW = p.mw;
                 ulonglong2 *out = p.gLL + (size_t)c * MW;            // + reader * G * MW
@@ -1064,7 +1121,7 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                         }
                         const int rd = j >> p.cs_shift;
                         const int jj = j & (cs - 1);
-                        LL::put(out + (size_t)rd * G * MW + 4 + jj * WPC, sr, sq, tag);
+                        LL::put(out + (size_t)rd * G * MW + jj * WPC, sr, sq, tag);
                     }
                 } else {
                     // columns past ld (readers' padding columns) still have to carry the tag
@@ -1072,132 +1129,113 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                     for (int j = (TRANS ? nt * p.TJ : ncg * V) + tid; j < G * cs; j += NTC) {
                         const int rd = j >> p.cs_shift;
                         const int jj = j & (cs - 1);
-                        LL::put(out + (size_t)rd * G * MW + 4 + jj * WPC, (T)0, (T)0, tag);
+                        LL::put(out + (size_t)rd * G * MW + jj * WPC, (T)0, (T)0, tag);
                     }
-                }
-                const int npad = MW - 4 - cs * WPC;                     // 1..4 padding words
-#pragma unroll 1
-                for (int e2 = tid; e2 < G * 8; e2 += NTC) {
-                    const int rd = e2 >> 3, k = e2 & 7;
-                    if (k < 4) ll_st_dbl(out + (size_t)rd * G * MW + k, ctl->sp[k], tag);
-                    else if (k - 4 < npad) ll_st(out + (size_t)rd * G * MW + MW - 1 - (k - 4), ll_pack(0u, tag), ll_pack(0u, tag));
                 }
             }
-            if (trace && !drain) trace[step * NTRACE + 2] = globaltimer_ns() - t_start;
+            if (tid == 0 && p.gate_mode == 1) *(volatile long long *)&ctl->gate = step + 1;
+            if (trace && !drain) trace[step * NTRACE + 2] = tstamp() - c_start;
 
             // ---------------- gather -------------------------------------------------------
-            // My inbox (G messages, contiguous) is fetched by one bulk copy into the held slot;
-            // every thread checks the tags of a few words, a thread that finds one missing polls
-            // that word in L2 and the fetch is repeated.  Then warp vc sums "virtual column" vc
-            // (vc < 4: scalar vc, else my column vc-4) over the sources, lanes = sources, in a
-            // fixed order.  Inboxes larger than a slot are processed in groups of p.gc sources.
+            // Straight from L2 into registers, no landing area and no TMA (the ring and the TMA
+            // queue stay free for the tiles of pass 2, which the producer stages meanwhile):
+            // thread = (message word k = tid % MW, writers tid / MW + i * NTC / MW), up to NB loads
+            // in flight, issued as one batch; a word whose tags do not match yet had not been
+            // written when the load read it and is polled by itself.  Each thread adds its words
+            // in writer order, the threads of a word are combined by a fixed shuffle tree and a
+            // fixed-order sum over the warps: bitwise deterministic.  (The four line-search scalars
+            // are not part of this exchange any more: the scalar warp reduces them during pass 1.)
+            double g_r = 0.0, g_q = 0.0;
             {
-                const int MW = p.mw;
-                ulonglong2 *stage = reinterpret_cast<ulonglong2 *>(ring + (size_t)hold_slot * p.slot_bytes);
-                const int nvc = 4 + cs;
+                const int MW = p.mw, wshift = p.mw_shift;
+                const int kq = tid & (MW - 1), wstride = NTC >> wshift;
+                const ulonglong2 *inb = inbox + kq;                   // + writer * MW
+                double a0 = 0.0, a1 = 0.0;
+                waiter.spins = 0;
 #pragma unroll 1
-                for (int g0 = 0; g0 < G; g0 += p.gc) {
-                    const int gn = min(p.gc, G - g0);
-                    const ulonglong2 *srcw = inbox + (size_t)g0 * MW;
-                    const int nwords = gn * MW;
-                    if (tid == 0) {
-                        mbar_expect_tx(xbar, (uint32_t)nwords * 16u);
-                        tma_bulk_g2s(stage, srcw, (uint32_t)nwords * 16u, xbar);
-                        if (p.gate_mode == 1) *(volatile long long *)&ctl->gate = step + 1;
+                for (int base = tid >> wshift; base < G; base += wstride * NB) {
+                    ulonglong2 v[NB];
+                    unsigned miss = 0;
+#pragma unroll
+                    for (int i = 0; i < NB; ++i) {
+                        const int wr = base + wstride * i;
+                        if (wr < G) { v[i] = ll_ld(inb + (size_t)wr * MW); miss |= 1u << i; }
                     }
-                    mbar_wait(xbar, xphase);
-                    xphase ^= 1u;
-                    if (trace && !drain) trace[step * NTRACE + 10] = globaltimer_ns() - t_start;
-                    unsigned missing = 0;
-                    {
-                        int i = 0;
-#pragma unroll 2
-                        for (int e = tid; e < nwords; e += NTC, ++i)
-                            if (!ll_ok(stage[e], tag)) missing |= 1u << i;
-                    }
-                    if (trace && !drain) trace[step * NTRACE + 11] = __popc(missing);
-                    if (missing && !(DBG & 1)) {
-                        waiter.begin(((long long)step << 32) | ((long long)(g0 * MW + tid) & 0xffffffff));
-                        ll_repair(stage, srcw, tid, missing, tag, waiter);
-                    }
-                    if (trace && !drain) trace[step * NTRACE + 12] = globaltimer_ns() - t_start;
-                    const bool gab = cbar_or(*(volatile int *)&ctl->abort != 0);   // repaired words visible
-                    if (trace && !drain) trace[step * NTRACE + 13] = globaltimer_ns() - t_start;
-                    if (gab) break;
-                    // column sums: warp = a pair of adjacent message words (2pr, 2pr+1), lane =
-                    // (source lane/2 + 16i, word lane%2).  The message length is 2 (mod 4) words, so
-                    // the 8 lanes of a quarter warp hit 8 different 16-byte bank groups.  Straight-line
-                    // on purpose: the loads go out as one batch (a branch per load serialises the
-                    // shared-memory latencies: measured 1.4 us instead of 0.3 us per step); lanes
-                    // past the last source read a padding word, which decodes to zero.
-                    {
-                        const int sub = lane & 1, srcl = lane >> 1;
-                        const int nwd = 4 + cs * WPC;
-                        double *csd = reinterpret_cast<double *>(colsum);
+                    const unsigned have = miss;
+#pragma unroll
+                    for (int i = 0; i < NB; ++i)
+                        if (((miss >> i) & 1u) && ll_ok(v[i], tag)) miss &= ~(1u << i);
+                    if (miss && !(DBG & 1)) {
+                        waiter.begin(((long long)step << 32) | ((long long)(base * MW + kq) & 0x7fffffff));
 #pragma unroll 1
-                        for (int pr = wid; 2 * pr < nwd; pr += NW) {
-                            const int word = 2 * pr + sub;
-                            ulonglong2 w[NLD];
+                        do {
 #pragma unroll
-                            for (int i = 0; i < NLD; ++i) {
-                                const int src = srcl + 16 * i;
-                                w[i] = stage[src < gn ? src * MW + word : MW - 1];
-                            }
-                            const bool dbl = WPC == 2 || pr < 2;     // fp64 words (warp-uniform)
-                            const bool has_max = dbl && pr == 1;     // word 3 is a maximum
-                            double a0 = 0.0, a1 = 0.0;
-                            if (dbl) {
+                            for (int i = 0; i < NB; ++i)
+                                if ((miss >> i) & 1u) v[i] = ll_ld(inb + (size_t)(base + wstride * i) * MW);
 #pragma unroll
-                                for (int i = 0; i < NLD; ++i) a0 += ll_dbl(w[i]);
-                                if (has_max) {
+                            for (int i = 0; i < NB; ++i)
+                                if (((miss >> i) & 1u) && ll_ok(v[i], tag)) miss &= ~(1u << i);
+                        } while (miss && waiter.again());
+                    }
 #pragma unroll
-                                    for (int i = 0; i < NLD; ++i) a1 = fmax(a1, ll_dbl(w[i]));
-                                }
+                    for (int i = 0; i < NB; ++i) {
+                        if ((have >> i) & 1u) {
+                            if (WPC == 2) {
+                                a0 += ll_dbl(v[i]);
                             } else {
-#pragma unroll
-                                for (int i = 0; i < NLD; ++i) {
-                                    a0 += (double)__uint_as_float((uint32_t)w[i].x);
-                                    a1 += (double)__uint_as_float((uint32_t)w[i].y);
-                                }
-                            }
-#pragma unroll
-                            for (int o = 2; o < 32; o <<= 1) {
-                                const double oa = __shfl_xor_sync(0xffffffffu, a0, o);
-                                const double ob = __shfl_xor_sync(0xffffffffu, a1, o);
-                                a0 += oa;
-                                a1 = has_max ? fmax(a1, ob) : a1 + ob;
-                            }
-                            if (lane < 2 && word < nwd) {
-                                if (dbl) {
-                                    // scalar k -> colsum[k].x; fp64 column j -> colsum[4 + j].(x | y)
-                                    const int at = word < 4 ? 2 * word : 2 * (4 + ((word - 4) >> 1)) + sub;
-                                    double v = word == 3 ? a1 : a0;
-                                    if (g0 > 0) v = word == 3 ? fmax(v, csd[at]) : v + csd[at];
-                                    csd[at] = v;
-                                } else {
-                                    if (g0 > 0) {
-                                        const double2 o = colsum[word];
-                                        a0 += o.x;
-                                        a1 += o.y;
-                                    }
-                                    colsum[word] = make_double2(a0, a1);
-                                }
+                                a0 += (double)__uint_as_float((uint32_t)v[i].x);
+                                a1 += (double)__uint_as_float((uint32_t)v[i].y);
                             }
                         }
                     }
-                    if (trace && !drain) trace[step * NTRACE + 14] = globaltimer_ns() - t_start;
-                    if (g0 + p.gc < G) cbar();     // the next group overwrites the landing area
+                }
+                if (trace && !drain) trace[step * NTRACE + 10] = tstamp() - c_start;
+                if (trace && !drain) trace[step * NTRACE + 11] = waiter.spins;
+                // the threads of one word: lanes k, k + MW, .. of a warp, then the warps
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    if (o >= MW) {
+                        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                        if (WPC == 1) a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                    }
+                }
+                red[tid] = make_double2(a0, a1);
+                cbar();
+                if (trace && !drain) trace[step * NTRACE + 12] = tstamp() - c_start;
+                // column threads: their column, warps in order
+                if (tid < cs) {
+                    // (at most NW partials per word: one per warp, or one per NTC / MW threads)
+                    const int stepk = MW < 32 ? 32 : MW;
+                    double2 v0[NW], v1[NW];
+#pragma unroll
+                    for (int j = 0; j < NW; ++j) {
+                        const int e = min(tid * WPC + stepk * j, NTC - WPC);
+                        v0[j] = red[e];
+                        v1[j] = red[e + (WPC - 1)];
+                    }
+#pragma unroll
+                    for (int j = 0; j < NW; ++j) {
+                        if (tid * WPC + stepk * j < NTC) {
+                            g_r += v0[j].x;
+                            g_q += WPC == 2 ? v1[j].x : v0[j].y;
+                        }
+                    }
                 }
             }
-            cbar();
             if (tid == 0 && p.gate_mode == 2) *(volatile long long *)&ctl->gate = step + 1;
-            if (trace && !drain) trace[step * NTRACE + 3] = trace[step * NTRACE + 4] = globaltimer_ns() - t_start;
+            if (trace && !drain) trace[step * NTRACE + 3] = trace[step * NTRACE + 4] = tstamp() - c_start;
 
             // ---------------- resolve the pending step: error, stop rule, gamma ---------
             bool go = true;
             double gamma_prev = 0.0;
             if (have_prev) {
-                const double rq = colsum[0].x, qq = colsum[1].x, l1 = colsum[2].x, err = colsum[3].x;
+                // the scalars of the pending step, summed over all CTAs by the scalar warp during pass 1
+                while (*(volatile long long *)&ctl->sc_done < step) {
+                    if (*(volatile int *)&ctl->abort) break;
+                }
+                __threadfence_block();
+                const double rq = *(volatile double *)&ctl->tot[0], qq = *(volatile double *)&ctl->tot[1],
+                             l1 = *(volatile double *)&ctl->tot[2], err = *(volatile double *)&ctl->tot[3];
                 if (c == 0 && tid == 0 && p.err_hist) p.err_hist[step_prev] = err;
                 if (p.bounded) {                                   // lasso.py:141-150
                     if (err < p.err_bound) ++block_cnt;
@@ -1210,11 +1248,11 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                     gamma_last = fmin(fmax(-(rq + mu * l1) / qq, 0.0), 1.0);
                 gamma_prev = gamma_last;
             }
-            if (trace && !drain) trace[step * NTRACE + 5] = globaltimer_ns() - t_start;
+            if (trace && !drain) trace[step * NTRACE + 5] = tstamp() - c_start;
 
             // ---------------- my column: apply the pending update, prox, publish D ------
+            double my_l1 = 0.0, my_err = 0.0, delta = 0.0;
             if (colthr) {
-                double my_l1 = 0.0, my_err = 0.0, delta = 0.0;
                 if (have_prev && go && prev_idx >= 0) {
                     const double xn = xprev + gamma_prev * dprev;                // lasso.py:153
                     __stcg(p.x + prev_idx, xn);
@@ -1225,8 +1263,7 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                 prev_idx = -1;
                 if (!drain) {
                     if (has_col && dj > 0.0) {
-                        const double2 cs2 = colsum[4 + tid];
-                        const double g = cs2.x + gamma_prev * cs2.y;
+                        const double g = g_r + gamma_prev * g_q;
                         const double u = dj * xj - g;                             // lasso.py:114
                         const double au = fabs(u) - mu;                           // cpu_calculation.py:5-6
                         const double soft = au > 0.0 ? copysign(au, u) : 0.0;
@@ -1240,52 +1277,84 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                         xprev = xj;
                         prev_idx = idx;
                     }
-                    LL::dput(p.dLL, jcol, (T)delta, tag);
-                    l1s[tid] = my_l1;
-                    es[tid] = my_err;
                 }
             }
-            // A CTA that owns no column publishes an acknowledgement word instead.  Nobody starts
-            // pass 2 before every word of this fetch is there, i.e. before EVERY CTA has finished
-            // its gather -- which is what allows a writer to overwrite inbox words next step.
-            if (!drain && tid == 0 && j0 >= ld) ll_st(p.dLL + ld + (c - p.nown), ll_pack(0u, tag), ll_pack(0u, tag));
-            if (trace && !drain) trace[step * NTRACE + 6] = globaltimer_ns() - t_start;
+            // D goes out in whole 32-byte sectors, one store per sector (the columns of a sector sit in
+            // adjacent lanes: the first lane collects the others' words).  Pieces of a sector written
+            // by different store instructions become visible MUCH later (measured: packing two columns
+            // per word with 8-byte stores cost 1.5 us per step).
+            if (!drain && wid * 32 < cs) {
+                unsigned long long w0, w1;
+                LL::dwords((T)delta, tag, w0, w1);
+                if (p.dsec && p.dpw == 2) {                    // four columns per sector
+                    const unsigned long long a1 = __shfl_down_sync(0xffffffffu, w0, 1);
+                    const unsigned long long a2 = __shfl_down_sync(0xffffffffu, w0, 2);
+                    const unsigned long long a3 = __shfl_down_sync(0xffffffffu, w0, 3);
+                    if (colthr && (lane & 3) == 0) ll_st2(p.dLL + (jcol >> 1), w0, a1, a2, a3);
+                } else if (p.dsec) {                           // two columns per sector
+                    const unsigned long long b0 = __shfl_down_sync(0xffffffffu, w0, 1);
+                    const unsigned long long b1 = __shfl_down_sync(0xffffffffu, w1, 1);
+                    if (colthr && (lane & 1) == 0) ll_st2(p.dLL + jcol, w0, w1, b0, b1);
+                } else if (colthr) {
+                    ll_st(p.dLL + jcol, w0, w1);
+                }
+            }
+            // A CTA that owns no column publishes an acknowledgement (a sector of its own) instead.
+            // Nobody starts pass 2 before every word of this fetch is there, i.e. before EVERY CTA has
+            // finished its gather -- which is what allows a writer to overwrite inbox words next step.
+            if (!drain && tid == 0 && j0 >= ld) {
+                const unsigned long long tw = ll_pack(0u, tag);
+                ll_st2(p.dLL + p.ackbase + 2 * (c - p.nown), tw, tw, tw, tw);
+            }
+            if (trace && !drain) trace[step * NTRACE + 6] = tstamp() - c_start;
 
             // ---------------- the step D from all slice owners -------------------------
+            // every thread loads, checks, polls and decodes its own words (tid + i * NTC), NB in
+            // flight: no vote, no barrier until the decoded D is complete
             if (!drain) {
-                ulonglong2 *stage = reinterpret_cast<ulonglong2 *>(ring + (size_t)hold_slot * p.slot_bytes);
-                const int dtot = ld + (G - p.nown);        // D words + acknowledgements
+                const int dwords = ld / p.dpw;
+                const int dtot = p.ackbase + 2 * (G - p.nown);    // D words + acknowledgements
+                if (tid == 0 && p.gate_mode == 3) *(volatile long long *)&ctl->gate = step + 1;
 #pragma unroll 1
-                for (int w0 = 0; w0 < dtot; w0 += p.dchunk) {
-                    const int nwords = min(p.dchunk, dtot - w0);
-                    const ulonglong2 *srcw = p.dLL + w0;
-                    if (w0 > 0) cbar();            // the previous chunk has been decoded
-                    if (tid == 0) {
-                        mbar_expect_tx(xbar, (uint32_t)nwords * 16u);
-                        tma_bulk_g2s(stage, srcw, (uint32_t)nwords * 16u, xbar);
-                        if (p.gate_mode == 3) *(volatile long long *)&ctl->gate = step + 1;
+                for (int base = tid; base < dtot; base += NTC * NB) {
+                    ulonglong2 v[NB];
+                    unsigned miss = 0;
+#pragma unroll
+                    for (int i = 0; i < NB; ++i) {
+                        const int e = base + NTC * i;
+                        if (e < dtot && (e < dwords || e >= p.ackbase)) { v[i] = ll_ld(p.dLL + e); miss |= 1u << i; }
                     }
-                    mbar_wait(xbar, xphase);
-                    xphase ^= 1u;
-                    // every thread checks, repairs and then decodes its own words: no vote needed
-                    unsigned missing = 0;
-                    {
-                        int i = 0;
-#pragma unroll 4
-                        for (int e = tid; e < nwords; e += NTC, ++i)
-                            if (!ll_ok(stage[e], tag)) missing |= 1u << i;
+                    const unsigned have = miss;
+#pragma unroll
+                    for (int i = 0; i < NB; ++i)
+                        if (((miss >> i) & 1u) && ll_ok(v[i], tag)) miss &= ~(1u << i);
+                    if (miss && !(DBG & 1)) {
+                        waiter.begin(((long long)step << 32) | (1LL << 31) | (long long)base);
+#pragma unroll 1
+                        do {
+#pragma unroll
+                            for (int i = 0; i < NB; ++i)
+                                if ((miss >> i) & 1u) v[i] = ll_ld(p.dLL + base + NTC * i);
+#pragma unroll
+                            for (int i = 0; i < NB; ++i)
+                                if (((miss >> i) & 1u) && ll_ok(v[i], tag)) miss &= ~(1u << i);
+                        } while (miss && waiter.again());
                     }
-                    if (missing && !(DBG & 1)) {
-                        waiter.begin(((long long)step << 32) | (1LL << 31) | (long long)(w0 + tid));
-                        ll_repair(stage, srcw, tid, missing, tag, waiter);
+#pragma unroll
+                    for (int i = 0; i < NB; ++i) {
+                        const int e = base + NTC * i;
+                        if (((have >> i) & 1u) && e < dwords) LL::dget(v[i], p.dpw, delta_s + e * p.dpw);
                     }
-#pragma unroll 4
-                    for (int e = tid; e < nwords; e += NTC)
-                        if (w0 + e < ld) delta_s[w0 + e] = LL::dval(stage[e]);
+                }
+                // the l1 / err terms of my columns (the threads of the first cs / 32 warps), summed per
+                // warp here, where the warp would otherwise sit in the barrier; thread 0 adds the warps
+                if (wid * 32 < cs) {
+                    const double a = warp_sum(my_l1), e = warp_max(my_err);
+                    if (lane == 0) { l1s[wid] = a; es[wid] = e; }
                 }
             }
             cbar();
-            if (trace && !drain) trace[step * NTRACE + 7] = globaltimer_ns() - t_start;
+            if (trace && !drain) trace[step * NTRACE + 7] = tstamp() - c_start;
             if (*(volatile int *)&ctl->abort) {
                 aborted = 1;
                 break;
@@ -1295,23 +1364,21 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                 steps_done = step_prev + 1;
                 break;
             }
-            if (have_prev) {
+            // r += gamma q of the pending step (lasso.py:155).  Pass 2 does not read r: on one GPU the
+            // update rides in the loop after pass 2 that reads and writes the same entries anyway; with
+            // peers the collector warp reads r while pass 2 runs, so it is applied here
+            if (have_prev && (WORLD > 1 || drain)) {
 #pragma unroll 1
                 for (int i = tid; i < rows_c; i += NTC) {
-                    const double rn = r_loc[i] + gamma_prev * q_loc[i];   // lasso.py:155
+                    const double rn = r_loc[i] + gamma_prev * q_loc[i];
                     r_loc[i] = rn;
                     rT[i] = (T)rn;
                 }
             }
             if (drain) break;
-            if (nt > 0 && lane == 0) mbar_arrive(empty + hold_slot);   // the landing area goes back
             if (tid == 0) {
-                double a = 0.0, e = 0.0;
-                const int ncol = min(cs, max(0, ld - j0));
-#pragma unroll 1
-                for (int i = 0; i < ncol; ++i) { a += l1s[i]; e = fmax(e, es[i]); }
-                ctl->sp[2] = a;
-                ctl->sp[3] = e;
+                ctl->sp[2] = cs > 32 ? l1s[0] + l1s[1] : l1s[0];
+                ctl->sp[3] = cs > 32 ? fmax(es[0], es[1]) : es[0];
             }
             if (DK > 0) {
 #pragma unroll
@@ -1345,33 +1412,63 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
             OP::zero(accT);
             const int ivT = TRANS ? tid % p.BXV : 0, partT = TRANS ? tid / p.BXV : 0;
             {
-                // one row of the tile against D: partial sum of this lane's column groups
-                auto row_dot = [&](const T *trow) -> T {
-                    Acc a0, a1;
-                    OP::zero(a0);
-                    OP::zero(a1);
-                    if (DK > 0) {
+                // Rows of the tile against D.  Narrow blocks (D in registers): all loads of a row pair
+                // go out as one batch (NK per row: the smallest of 2 / 4 / 8 that covers the block; a
+                // lane past the last column group reads the last one against a zero D) and only then
+                // the multiply-adds -- a load / use / load chain leaves the two warps of a scheduler
+                // waiting for shared memory most of the time.
+                auto pair_dot = [&](auto nk_tag, const T *rowa, const T *rowb, T &qa, T &qb) {
+                    constexpr int NK = decltype(nk_tag)::value;
+                    VecT va[NK], vb[NK];
 #pragma unroll
-                        for (int k = 0; k < DK; k += 2) {
-                            if (k < dk_n) {
-                                const int cga = min(lane + 32 * k, ncg - 1);          // dreg is 0 past ncg
-                                const int cgb = min(lane + 32 * (k + 1), ncg - 1);
-                                const VecT va = *reinterpret_cast<const VecT *>(trow + cga * V);
-                                const VecT vb = *reinterpret_cast<const VecT *>(trow + cgb * V);
-                                OP::mac(a0, va, dreg[k]);
-                                OP::mac(a1, vb, dreg[k + 1 < DK ? k + 1 : k]);
-                            }
-                        }
+                    for (int k = 0; k < NK; ++k) {
+                        const int cg = min(lane + 32 * k, ncg - 1);
+                        va[k] = *reinterpret_cast<const VecT *>(rowa + cg * V);
+                        vb[k] = *reinterpret_cast<const VecT *>(rowb + cg * V);
+                    }
+                    Acc a0, a1, b0, b1;
+                    OP::zero(a0); OP::zero(a1); OP::zero(b0); OP::zero(b1);
+#pragma unroll
+                    for (int k = 0; k < NK; ++k) {
+                        const VecT d = dreg[k < (DK > 0 ? DK : 1) ? k : 0];
+                        if (k & 1) { OP::mac(a1, va[k], d); OP::mac(b1, vb[k], d); }
+                        else       { OP::mac(a0, va[k], d); OP::mac(b0, vb[k], d); }
+                    }
+                    qa = OP::hsum(a0) + OP::hsum(a1);
+                    qb = OP::hsum(b0) + OP::hsum(b1);
+                };
+                auto row_pair = [&](const T *rowa, const T *rowb, T &qa, T &qb) {
+                    if (DK > 0) {
+                        if (dk_n > 4) pair_dot(std::integral_constant<int, 8>(), rowa, rowb, qa, qb);
+                        else if (dk_n > 2) pair_dot(std::integral_constant<int, 4>(), rowa, rowb, qa, qb);
+                        else pair_dot(std::integral_constant<int, 2>(), rowa, rowb, qa, qb);
                     } else {
+                        // wide blocks: D from shared memory, two rows share every D load
+                        Acc a0, b0;
+                        OP::zero(a0); OP::zero(b0);
 #pragma unroll 2
                         for (int cg = lane; cg < ncg; cg += 32) {
-                            const VecT v0 = *reinterpret_cast<const VecT *>(trow + cg * V);
                             const VecT d0 = *reinterpret_cast<const VecT *>(delta_s + cg * V);
-                            OP::mac(a0, v0, d0);
+                            OP::mac(a0, *reinterpret_cast<const VecT *>(rowa + cg * V), d0);
+                            OP::mac(b0, *reinterpret_cast<const VecT *>(rowb + cg * V), d0);
                         }
+                        qa = OP::hsum(a0);
+                        qb = OP::hsum(b0);
                     }
-                    return OP::hsum(a0) + OP::hsum(a1);
                 };
+                // a finished pair: sum over the lanes (a in lanes 0..15, b in 16..31), store, send
+                auto flush_pair = [&](int row_a, bool two, T qa, T qb) {
+                    const T qs = warp_sum_pair(qa, qb, lane);
+                    if (row_a >= 0 && (lane & 15) == 0 && (two || lane == 0)) {
+                        const int row = row_a + (lane >> 4) * NW;
+                        qpart[row] = (double)qs;
+                        if (p.xmode == 1) send_row(row, (double)qs);
+                    }
+                };
+                if (trace) trace[step * NTRACE + 14] = tstamp() - c_start;
+                T pqa = (T)0, pqb = (T)0;
+                int pend_row = -1;
+                bool pend_two = false;
 #pragma unroll 1
                 for (int t2 = 0; t2 < nt; ++t2) {
                     const int t = t2;
@@ -1379,7 +1476,7 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                     const int slot = cur.slot;
                     cur.advance(S);
                     ++kc;
-                    if (ttrace && t2 < 16) ttrace[step * NTTRACE + 32 + t2] = globaltimer_ns();
+                    if (ttrace && t2 < 16) ttrace[step * NTTRACE + 32 + t2] = tstamp();
                     const T *tile = reinterpret_cast<const T *>(ring + (size_t)slot * p.slot_bytes);
                     const int rows_t = min(TR, rows_c - t * TR);
                     if (TRANS) {
@@ -1393,23 +1490,22 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                             }
                         }
                     } else if (!(DBG & 4)) {
-                        int rr = wid;
+                        // two rows per trip (the odd last row is paired with itself).  The shuffle tree
+                        // of a pair is a chain of dependent instructions: it runs one trip late, under
+                        // the loads of the next pair (multi-GPU: at once, the peers wait for the rows)
 #pragma unroll 1
-                        for (; rr + NW < rows_t; rr += 2 * NW) {      // two rows per trip
-                            const T qa = row_dot(tile + (size_t)rr * ld);
-                            const T qb = row_dot(tile + (size_t)(rr + NW) * ld);
-                            const T qs = warp_sum_pair(qa, qb, lane);
-                            if ((lane & 15) == 0) {
-                                const int row = t * TR + rr + (lane >> 4) * NW;
-                                qpart[row] = (double)qs;
-                                if (p.xmode == 1) send_row(row, (double)qs);
-                            }
-                        }
-                        if (rr < rows_t) {
-                            const T qs = warp_sum(row_dot(tile + (size_t)rr * ld));
-                            if (lane == 0) {
-                                qpart[t * TR + rr] = (double)qs;
-                                if (p.xmode == 1) send_row(t * TR + rr, (double)qs);
+                        for (int rr = wid; rr < rows_t; rr += 2 * NW) {
+                            const bool two = rr + NW < rows_t;
+                            T qa, qb;
+                            if (WORLD == 1) {
+                                // (unconditional, only the store is predicated: one basic block, so that
+                                // the loads below are scheduled over the shuffle chain)
+                                flush_pair(pend_row, pend_two, pqa, pqb);
+                                row_pair(tile + (size_t)rr * ld, tile + (size_t)(two ? rr + NW : rr) * ld, qa, qb);
+                                pqa = qa; pqb = qb; pend_row = t * TR + rr; pend_two = two;
+                            } else {
+                                row_pair(tile + (size_t)rr * ld, tile + (size_t)(two ? rr + NW : rr) * ld, qa, qb);
+                                flush_pair(t * TR + rr, two, qa, qb);
                             }
                         }
                         if (WORLD > 1 && p.xmode == 0) {
@@ -1424,8 +1520,9 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(empty + slot);
-                    if (ttrace && t2 < 16) ttrace[step * NTTRACE + 48 + t2] = globaltimer_ns();
+                    if (ttrace && t2 < 16) ttrace[step * NTTRACE + 48 + t2] = tstamp();
                 }
+                if (!TRANS) flush_pair(pend_row, pend_two, pqa, pqb);
             }
             if (TRANS) {
                 // combine the column parts through shared memory
@@ -1443,7 +1540,7 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
             } else {
                 cbar();
             }
-            if (trace) trace[step * NTRACE + 8] = globaltimer_ns() - t_start;
+            if (trace) trace[step * NTRACE + 8] = tstamp() - c_start;
             if (WORLD > 1) {
                 // multi-GPU: my partial rows are complete (and sent); the collector warp sums them
                 // with the peers' rows and computes the line-search partials while the next step's
@@ -1455,12 +1552,16 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
             } else
             {
                 double trq = 0.0, tqq = 0.0;
+                const double gp = have_prev ? gamma_prev : 0.0;
 #pragma unroll 1
                 for (int i = tid; i < rows_c; i += NTC) {
+                    const double rn = r_loc[i] + gp * q_loc[i];              // lasso.py:155 (pending step)
                     const double q = qpart[i];
+                    r_loc[i] = rn;
+                    rT[i] = (T)rn;
                     q_loc[i] = q;
                     qT[i] = (T)q;
-                    trq += r_loc[i] * q;                                     // lasso.py:129
+                    trq += rn * q;                                           // lasso.py:129
                     tqq += q * q;                                            // lasso.py:132
                 }
                 trq = warp_sum(trq);
@@ -1470,7 +1571,12 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
                 if (wid == 0) {
                     const double a = warp_sum(lane < NW ? lsred[lane] : 0.0);
                     const double b = warp_sum(lane < NW ? lsred[NW + lane] : 0.0);
-                    if (lane == 0) { ctl->sp[0] = a; ctl->sp[1] = b; }
+                    if (lane == 0) {
+                        ctl->sp[0] = a;
+                        ctl->sp[1] = b;
+                        __threadfence_block();
+                        *(volatile long long *)&ctl->sc_go = step + 1;   // the scalar warp takes them from here
+                    }
                 }
             }
             have_prev = true;
@@ -1478,9 +1584,14 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
             step_prev = step;
             steps_done = step + 1;
             if (c == 0 && tid == 0 && p.time_hist) p.time_hist[step] = globaltimer_ns() - t_start;
-            if (trace) trace[step * NTRACE + 9] = globaltimer_ns() - t_start;
+            if (trace) trace[step * NTRACE + 9] = tstamp() - c_start;
         }
 
+        if (trace && p.nsteps >= 2) {      // cycles -> time: a (globaltimer, cycle) pair at both ends of the launch
+            trace[13] = t_start;
+            trace[(p.nsteps - 1) * NTRACE + 13] = globaltimer_ns();
+            trace[(p.nsteps - 1) * NTRACE + 11] = tstamp() - c_start;
+        }
         if (WORLD > 1) {
             // the collector warp finishes the step it is working on (its waits are bounded) before
             // it is shown the stop flag
@@ -1520,14 +1631,19 @@ __global__ void __launch_bounds__(FULL ? NTHREADS_MG : NTHREADS, 1) lasso_fused(
 // ------------------------------------------------------------------------------------
 // plain (non-persistent) kernels: weighted column sums, row dots, reductions
 // ------------------------------------------------------------------------------------
-// part[chunk][col] = sum_{rows in chunk} A[row][col] * (SQ ? A[row][col] : vec[row])
+// part[y][chunk][col] = sum_{rows in chunk} A_y[row][col] * (SQ ? A_y[row][col] : vec[row]); blockIdx.y
+// selects one of several equally shaped matrices (the column blocks: diag(A^T A) of all blocks is
+// ONE launch)
 template <typename T, bool SQ>
 __global__ void __launch_bounds__(256) colwsum_partial(const T *__restrict__ A, int64_t M, int ncols,
                                                        int64_t ld, const double *__restrict__ vec,
-                                                       double *__restrict__ part, int rows_per_chunk) {
+                                                       double *__restrict__ part, int rows_per_chunk,
+                                                       int64_t mat_stride) {
     using VecT = typename VT<T>::type;
     constexpr int V = VT<T>::V;
     const int chunk = blockIdx.x;
+    A += (int64_t)blockIdx.y * mat_stride;
+    part += (int64_t)blockIdx.y * gridDim.x * ncols;
     const int64_t r0 = (int64_t)chunk * rows_per_chunk;
     const int64_t r1 = min(M, r0 + rows_per_chunk);
     const int ncg = ncols / V;  // ncols is a multiple of V (padded)
@@ -1553,21 +1669,38 @@ __global__ void __launch_bounds__(256) colwsum_partial(const T *__restrict__ A, 
     }
 }
 
-// out[col] (+)= sum_chunk part[chunk][col]   (fixed order: deterministic)
-__global__ void reduce_partials(const double *__restrict__ part, int nchunks, int ncols,
-                                double *__restrict__ out, int accumulate) {
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= ncols) return;
+// out[y * out_stride + col] (+)= sum_chunk part[y][chunk][col], fixed order (deterministic):
+// 32 columns x 8 chunk groups per CTA, each thread adds every 8th chunk, thread row 0 adds the 8
+__global__ void __launch_bounds__(256) reduce_partials(const double *__restrict__ part, int nchunks, int ncols,
+                                                       double *__restrict__ out, int accumulate, int64_t out_stride) {
+    __shared__ double sm[8][33];
+    const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + cx;
+    part += (int64_t)blockIdx.y * nchunks * ncols;
     double s = 0.0;
-    for (int ch = 0; ch < nchunks; ++ch) s += part[(int64_t)ch * ncols + col];
-    out[col] = accumulate ? out[col] + s : s;
+    if (col < ncols) {
+#pragma unroll 4
+        for (int ch = gy; ch < nchunks; ch += 8) s += part[(int64_t)ch * ncols + col];
+    }
+    sm[gy][cx] = s;
+    __syncthreads();
+    if (gy == 0 && col < ncols) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sm[k][cx];
+        double *o = out + (int64_t)blockIdx.y * out_stride + col;
+        *o = accumulate ? *o + t : t;
+    }
 }
 
-// out[row] (+)= sum_col A[row][col] * (SQ ? A[row][col] : vec[col]); one warp per row
+// out[row] (+)= sum_col A[row][col] * (SQ ? A[row][col] : vec[col]); one warp per row.  Rows are
+// written to out[(row / group) * out_stride + row % group] (group = rows per column block when
+// the rows of all blocks are processed in one launch)
 template <typename T, bool SQ>
 __global__ void __launch_bounds__(256) rowdot_kernel(const T *__restrict__ A, int64_t M, int ncols,
                                                      int64_t ld, const double *__restrict__ vec,
-                                                     double *__restrict__ out, int accumulate) {
+                                                     double *__restrict__ out, int accumulate, int64_t group,
+                                                     int64_t out_stride) {
     using VecT = typename VT<T>::type;
     constexpr int V = VT<T>::V;
     const int lane = threadIdx.x & 31;
@@ -1575,16 +1708,30 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const T *__restrict__ A, in
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int ncg = ncols / V;
     for (int64_t r = warp; r < M; r += nwarps) {
-        double acc = 0.0;
-        for (int cg = lane; cg < ncg; cg += 32) {
+        double acc0 = 0.0, acc1 = 0.0;
+        int cg = lane;
+        for (; cg + 32 < ncg; cg += 64) {                // two independent 16-byte loads per trip
+            const VecT v = __ldg(reinterpret_cast<const VecT *>(A + r * ld + (int64_t)cg * V));
+            const VecT u = __ldg(reinterpret_cast<const VecT *>(A + r * ld + (int64_t)(cg + 32) * V));
+            const T *ve = reinterpret_cast<const T *>(&v);
+            const T *ue = reinterpret_cast<const T *>(&u);
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                acc0 += (double)ve[e] * (SQ ? (double)ve[e] : vec[cg * V + e]);
+                acc1 += (double)ue[e] * (SQ ? (double)ue[e] : vec[(cg + 32) * V + e]);
+            }
+        }
+        if (cg < ncg) {
             const VecT v = __ldg(reinterpret_cast<const VecT *>(A + r * ld + (int64_t)cg * V));
             const T *ve = reinterpret_cast<const T *>(&v);
 #pragma unroll
-            for (int e = 0; e < V; ++e)
-                acc += (double)ve[e] * (SQ ? (double)ve[e] : vec[cg * V + e]);
+            for (int e = 0; e < V; ++e) acc0 += (double)ve[e] * (SQ ? (double)ve[e] : vec[cg * V + e]);
         }
-        acc = warp_sum(acc);
-        if (lane == 0) out[r] = accumulate ? out[r] + acc : acc;
+        const double acc = warp_sum(acc0 + acc1);
+        if (lane == 0) {
+            double *o = out + (r / group) * out_stride + r % group;
+            *o = accumulate ? *o + acc : acc;
+        }
     }
 }
 
@@ -1735,7 +1882,7 @@ struct b200l_ctx {
     double *vin, *vout, *part;
     int part_chunks;
     // cross-CTA exchange buffers of the fused kernel (LL words, see above)
-    ulonglong2 *gLL, *dLL;
+    ulonglong2 *gLL, *dLL, *sLL;
     size_t gLL_bytes;
     int *abort_flag;
     uint32_t tag_base;            // tags already used by earlier launches
@@ -1746,7 +1893,7 @@ struct b200l_ctx {
     int32_t *order;
     int64_t hist_cap, order_cap;
     int64_t step_counter;
-    int have_problem;
+    int have_problem, have_diag;
     cudaEvent_t ev0, ev1;
     // tuning
     int32_t slot_target, max_inflight, dbg;
@@ -1756,6 +1903,8 @@ struct b200l_ctx {
     int world, rank;
     ulonglong2 *peer[B200L_MAX_WORLD];   // peer[rank] = own inbox (cudaMalloc), others IPC-mapped
     size_t inbox_bytes;
+    int peer_ipc;                        // the inboxes are CUDA IPC mappings owned by this library
+    ulonglong2 *mc;                      // multicast (NVLS) mapping of all ranks' inboxes, or NULL
     // cached geometry
     RunParams geo;
     int grid, smem_bytes, cpt, nt_max;
@@ -1851,12 +2000,14 @@ extern "C" int b200l_ctx_create(b200l_ctx **out, int dtype, int layout, int64_t 
     ALLOC(c->d, nx * 8);
     ALLOC(c->drec, nx * 8);
     ALLOC(c->dsum, nx * 8);
-    ALLOC(c->r, N * 8);
-    ALLOC(c->b, N * 8);
+    const int64_t npad = round_up(N, 4) + 4;   // the pre-transposed layout reduces ld >= N entries into r
+    ALLOC(c->r, npad * 8);
+    ALLOC(c->b, npad * 8);
     ALLOC(c->vin, vmax * 8);
     ALLOC(c->vout, vmax * 8);
     ALLOC(c->part, (int64_t)c->part_chunks * part_cols * 8);
-    ALLOC(c->dLL, (c->xld + GMAX) * 16);
+    ALLOC(c->dLL, (c->xld + 2 * GMAX + 2) * 16);
+    ALLOC(c->sLL, GMAX * 4 * 16);
     ALLOC(c->abort_flag, 64);
     ALLOC(c->gamma_state, 8);
     ALLOC(c->objbuf, 64);
@@ -1865,11 +2016,12 @@ extern "C" int b200l_ctx_create(b200l_ctx **out, int dtype, int layout, int64_t 
     CK(cudaMemset(c->x, 0, nx * 8));
     CK(cudaMemset(c->d, 0, nx * 8));
     CK(cudaMemset(c->drec, 0, nx * 8));
-    CK(cudaMemset(c->r, 0, N * 8));
-    CK(cudaMemset(c->b, 0, N * 8));
+    CK(cudaMemset(c->r, 0, npad * 8));
+    CK(cudaMemset(c->b, 0, npad * 8));
     CK(cudaMemset(c->gamma_state, 0, 8));
     CK(cudaMemset(c->state, 0, 64));
-    CK(cudaMemset(c->dLL, 0, (size_t)(c->xld + GMAX) * 16));
+    CK(cudaMemset(c->dLL, 0, (size_t)(c->xld + 2 * GMAX + 2) * 16));
+    CK(cudaMemset(c->sLL, 0, (size_t)GMAX * 4 * 16));
     CK(cudaMemset(c->abort_flag, 0, 64));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
@@ -1883,7 +2035,7 @@ extern "C" int b200l_ctx_destroy(b200l_ctx *c) {
     cudaStreamSynchronize(c->stream);
     comm_release(c);
     void *ptrs[] = {c->x, c->d, c->drec, c->dsum, c->r, c->b, c->vin, c->vout, c->part, c->gLL,
-                    c->dLL, c->abort_flag, c->gamma_state, c->objbuf, c->state, c->err_hist,
+                    c->dLL, c->sLL, c->abort_flag, c->gamma_state, c->objbuf, c->state, c->err_hist,
                     c->time_hist, c->trace, c->ttrace, c->order};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -1914,6 +2066,7 @@ extern "C" int b200l_ctx_bind_A(b200l_ctx *c, const void *A_dev) {
         return fail("A_dev is not a device pointer");
     c->A = A_dev;
     c->have_problem = 0;
+    c->have_diag = 0;
     c->tmap_valid = 0;
     return 0;
 }
@@ -1921,41 +2074,47 @@ extern "C" int b200l_ctx_bind_A(b200l_ctx *c, const void *A_dev) {
 // ------------------------------------------------------------------------------------
 // device-level mat-vecs on block m (vectors are device doubles)
 // ------------------------------------------------------------------------------------
+// nmat equally shaped matrices (stride mat_stride elements), results out[y * out_stride + col]
 template <typename T>
 static int colwsum_dev(b200l_ctx *c, const T *Ablk, int64_t M, int ncols, int64_t ld, const double *vec,
-                       double *out, bool sq, int accumulate) {
-    int chunks = (int)std::min<int64_t>(c->part_chunks, M);
+                       double *out, bool sq, int accumulate, int nmat = 1, int64_t mat_stride = 0,
+                       int64_t out_stride = 0) {
+    const int budget = std::max(1, c->part_chunks / nmat);
+    int chunks = (int)std::min<int64_t>(budget, M);
     int rpc = (int)((M + chunks - 1) / chunks);
     chunks = (int)((M + rpc - 1) / rpc);
+    const dim3 grid(chunks, nmat);
     if (sq)
-        colwsum_partial<T, true><<<chunks, 256, 0, c->stream>>>(Ablk, M, ncols, ld, vec, c->part, rpc);
+        colwsum_partial<T, true><<<grid, 256, 0, c->stream>>>(Ablk, M, ncols, ld, vec, c->part, rpc, mat_stride);
     else
-        colwsum_partial<T, false><<<chunks, 256, 0, c->stream>>>(Ablk, M, ncols, ld, vec, c->part, rpc);
-    reduce_partials<<<(ncols + 127) / 128, 128, 0, c->stream>>>(c->part, chunks, ncols, out, accumulate);
+        colwsum_partial<T, false><<<grid, 256, 0, c->stream>>>(Ablk, M, ncols, ld, vec, c->part, rpc, mat_stride);
+    reduce_partials<<<dim3((ncols + 31) / 32, nmat), 256, 0, c->stream>>>(c->part, chunks, ncols, out, accumulate,
+                                                                          out_stride);
     CK(cudaGetLastError());
     return 0;
 }
 
 template <typename T>
 static int rowdot_dev(b200l_ctx *c, const T *Ablk, int64_t M, int ncols, int64_t ld, const double *vec,
-                      double *out, bool sq, int accumulate) {
+                      double *out, bool sq, int accumulate, int64_t group = 0, int64_t out_stride = 0) {
     const int64_t warps = std::min<int64_t>(M, (int64_t)c->sm_count * 64);
     const int blocks = (int)((warps + 7) / 8);
+    if (group <= 0) { group = M; out_stride = 0; }
     if (sq)
-        rowdot_kernel<T, true><<<blocks, 256, 0, c->stream>>>(Ablk, M, ncols, ld, vec, out, accumulate);
+        rowdot_kernel<T, true><<<blocks, 256, 0, c->stream>>>(Ablk, M, ncols, ld, vec, out, accumulate, group, out_stride);
     else
-        rowdot_kernel<T, false><<<blocks, 256, 0, c->stream>>>(Ablk, M, ncols, ld, vec, out, accumulate);
+        rowdot_kernel<T, false><<<blocks, 256, 0, c->stream>>>(Ablk, M, ncols, ld, vec, out, accumulate, group, out_stride);
     CK(cudaGetLastError());
     return 0;
 }
 
 // g[xld] = A_m^T r[N]
 template <typename T>
-static int gemv_t_dev(b200l_ctx *c, int m, const double *r, double *g, bool sq) {
+static int gemv_t_dev(b200l_ctx *c, int m, const double *r, double *g) {
     const T *Ablk = reinterpret_cast<const T *>(c->A) + (int64_t)m * c->brows * c->ld;
     if (c->layout == B200L_ROWMAJOR)
-        return colwsum_dev<T>(c, Ablk, c->N, (int)c->ld, c->ld, r, g, sq, 0);
-    return rowdot_dev<T>(c, Ablk, c->w, (int)c->ld, c->ld, r, g, sq, 0);
+        return colwsum_dev<T>(c, Ablk, c->N, (int)c->ld, c->ld, r, g, false, 0);
+    return rowdot_dev<T>(c, Ablk, c->w, (int)c->ld, c->ld, r, g, false, 0);
 }
 // q[N] (+)= A_m d[xld]
 template <typename T>
@@ -1973,17 +2132,28 @@ static int need_A(b200l_ctx *c) {
     return 0;
 }
 
+// d = diag(A^T A) of every block in ONE pass over A (two or three launches in all); kept until another
+// matrix is bound or its entries change (gpu_calculation.py:246-261 recomputes it per call)
+template <typename T>
+static int compute_diag_t(b200l_ctx *c) {
+    const T *A = reinterpret_cast<const T *>(c->A);
+    if (c->layout == B200L_ROWMAJOR)
+        return colwsum_dev<T>(c, A, c->N, (int)c->ld, c->ld, nullptr, c->dsum, true, 0, c->nblocks,
+                              c->brows * c->ld, c->xld);
+    // transposed: the blocks are consecutive rows of one (nblocks * w) x ld matrix; the padding of
+    // a row (entries N .. ld-1) is zero
+    return rowdot_dev<T>(c, A, (int64_t)c->nblocks * c->w, (int)c->ld, c->ld, nullptr, c->dsum, true, 0, c->w, c->xld);
+}
+
 static int compute_diag(b200l_ctx *c) {
-    // the transposed layout pads N, so the row-dot must not see padding: it is zero-filled
-    for (int m = 0; m < c->nblocks; ++m) {
-        double *out = c->dsum + (int64_t)m * c->xld;
-        int rc = c->dtype == B200L_F32 ? gemv_t_dev<float>(c, m, nullptr, out, true)
-                                       : gemv_t_dev<double>(c, m, nullptr, out, true);
-        if (rc) return rc;
-    }
+    if (c->have_diag) return 0;
     const int64_t nx = (int64_t)c->nblocks * c->xld;
+    CK(cudaMemsetAsync(c->dsum, 0, (size_t)nx * 8, c->stream));
+    const int rc = c->dtype == B200L_F32 ? compute_diag_t<float>(c) : compute_diag_t<double>(c);
+    if (rc) return rc;
     finish_diag<<<(int)((nx + 255) / 256), 256, 0, c->stream>>>(c->dsum, c->d, c->drec, nx);
     CK(cudaGetLastError());
+    c->have_diag = 1;
     return 0;
 }
 
@@ -2004,8 +2174,8 @@ extern "C" int b200l_gemv_t(b200l_ctx *c, int32_t m, const double *r_host, doubl
     const int64_t nin = c->layout == B200L_ROWMAJOR ? c->N : c->ld;
     CK(cudaMemsetAsync(c->vin, 0, (size_t)nin * 8, c->stream));
     CK(cudaMemcpyAsync(c->vin, r_host, (size_t)c->N * 8, cudaMemcpyHostToDevice, c->stream));
-    int rc = c->dtype == B200L_F32 ? gemv_t_dev<float>(c, m, c->vin, c->vout, false)
-                                   : gemv_t_dev<double>(c, m, c->vin, c->vout, false);
+    int rc = c->dtype == B200L_F32 ? gemv_t_dev<float>(c, m, c->vin, c->vout)
+                                   : gemv_t_dev<double>(c, m, c->vin, c->vout);
     if (rc) return rc;
     CK(cudaMemcpyAsync(g_host, c->vout, (size_t)c->w * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -2023,6 +2193,51 @@ extern "C" int b200l_gemv_n(b200l_ctx *c, int32_t m, const double *d_host, doubl
     if (rc) return rc;
     CK(cudaMemcpyAsync(q_host, c->vout, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// device-vector variants: no staging copy, no synchronisation (the work is queued on the
+// context's stream).  r_dev needs N doubles (the pre-transposed layout reads ld >= N: the
+// vector has to be padded with zeros up to b200l_ctx_ld), g_dev gets w doubles.
+static int check_dev_ptr(const void *p, const char *what) {
+    cudaPointerAttributes attr;
+    CK(cudaPointerGetAttributes(&attr, p));
+    if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)
+        return fail("%s is not a device pointer", what);
+    return 0;
+}
+
+extern "C" int b200l_gemv_t_dev(b200l_ctx *c, int32_t m, const double *r_dev, double *g_dev) {
+    if (need_A(c)) return 1;
+    if (m < 0 || m >= c->nblocks) return fail("block index %d out of range", m);
+    if (!r_dev || !g_dev) return fail("NULL vector");
+    if (check_dev_ptr(r_dev, "r_dev") || check_dev_ptr(g_dev, "g_dev")) return 1;
+    const double *rin = r_dev;
+    if (c->layout == B200L_TRANSPOSED && c->ld != c->N) {     // zero-padded copy for the 16-byte row reads
+        CK(cudaMemsetAsync(c->vin, 0, (size_t)c->ld * 8, c->stream));
+        CK(cudaMemcpyAsync(c->vin, r_dev, (size_t)c->N * 8, cudaMemcpyDeviceToDevice, c->stream));
+        rin = c->vin;
+    }
+    int rc = c->dtype == B200L_F32 ? gemv_t_dev<float>(c, m, rin, c->vout) : gemv_t_dev<double>(c, m, rin, c->vout);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(g_dev, c->vout, (size_t)c->w * 8, cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+
+extern "C" int b200l_gemv_n_dev(b200l_ctx *c, int32_t m, const double *d_dev, double *q_dev) {
+    if (need_A(c)) return 1;
+    if (m < 0 || m >= c->nblocks) return fail("block index %d out of range", m);
+    if (!d_dev || !q_dev) return fail("NULL vector");
+    if (check_dev_ptr(d_dev, "d_dev") || check_dev_ptr(q_dev, "q_dev")) return 1;
+    const double *din = d_dev;
+    if (c->xld != c->w) {                                     // zero-padded copy for the 16-byte row reads
+        CK(cudaMemsetAsync(c->vin, 0, (size_t)c->xld * 8, c->stream));
+        CK(cudaMemcpyAsync(c->vin, d_dev, (size_t)c->w * 8, cudaMemcpyDeviceToDevice, c->stream));
+        din = c->vin;
+    }
+    int rc = c->dtype == B200L_F32 ? gemv_n_dev<float>(c, m, din, c->vout, 0) : gemv_n_dev<double>(c, m, din, c->vout, 0);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(q_dev, c->vout, (size_t)c->N * 8, cudaMemcpyDeviceToDevice, c->stream));
     return 0;
 }
 
@@ -2057,6 +2272,7 @@ extern "C" int b200l_gen_gaussian(b200l_ctx *c, uint64_t seed, int32_t rank, int
                                          : gen_dispatch<double>(c, 0, seed, rank, world, nullptr, nullptr);
     if (rc) return rc;
     c->have_problem = 0;
+    c->have_diag = 0;
     CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -2080,6 +2296,7 @@ extern "C" int b200l_scale_rows(b200l_ctx *c, const double *scale_host) {
                                          : gen_dispatch<double>(c, 2, 0, 0, 1, c->vin, nullptr);
     if (rc) return rc;
     c->have_problem = 0;
+    c->have_diag = 0;
     CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -2102,10 +2319,8 @@ extern "C" int b200l_set_problem(b200l_ctx *c, const double *b_host) {
     if (need_A(c)) return 1;
     if (!b_host) return fail("b_host is NULL");
     CK(cudaMemcpyAsync(c->b, b_host, (size_t)c->N * 8, cudaMemcpyHostToDevice, c->stream));
-    if (!c->have_problem) {
-        if (compute_diag(c)) return 1;
-        c->have_problem = 1;
-    }
+    if (compute_diag(c)) return 1;          // no-op when b200l_diag_ata already ran on this matrix
+    c->have_problem = 1;
     return reset_state(c);
 }
 
@@ -2173,6 +2388,38 @@ extern "C" int b200l_objective(b200l_ctx *c, double mu, double *value) {
     CK(cudaMemcpyAsync(h, c->objbuf, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     *value = h[0];
+    return 0;
+}
+
+// the two terms separately: with column shards over several GPUs every rank holds the full
+// residual (rss is the global 0.5*|Ax-b|^2 when halved) but only its slice of x, so the l1
+// term has to be summed over the ranks by the caller (path.lasso_path and bench.py do)
+extern "C" int b200l_objective_terms(b200l_ctx *c, double *rss, double *l1) {
+    if (!c || !rss || !l1) return fail("NULL argument");
+    CK(cudaSetDevice(c->device));
+    objective_kernel<<<1, 1024, 0, c->stream>>>(c->r, c->N, c->x, (int64_t)c->nblocks * c->xld, 0.0, c->objbuf);
+    CK(cudaGetLastError());
+    double h[3];
+    CK(cudaMemcpyAsync(h, c->objbuf, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *rss = h[1];
+    *l1 = h[2];
+    return 0;
+}
+
+// caller-supplied diagonal (the d_ATA argument of the solver classes, lasso.py:26-30) instead of
+// the one computed from the bound matrix: d (nblocks, w) doubles, 1/d taken like lasso.py:29-30
+extern "C" int b200l_set_diag(b200l_ctx *c, const double *d_host) {
+    if (need_A(c)) return 1;
+    if (!d_host) return fail("d_host is NULL");
+    const int64_t nx = (int64_t)c->nblocks * c->xld;
+    CK(cudaMemsetAsync(c->dsum, 0, (size_t)nx * 8, c->stream));
+    CK(cudaMemcpy2DAsync(c->dsum, (size_t)c->xld * 8, d_host, (size_t)c->w * 8, (size_t)c->w * 8,
+                         (size_t)c->nblocks, cudaMemcpyHostToDevice, c->stream));
+    finish_diag<<<(int)((nx + 255) / 256), 256, 0, c->stream>>>(c->dsum, c->d, c->drec, nx);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    c->have_diag = 1;
     return 0;
 }
 
@@ -2278,7 +2525,6 @@ static int plan_geometry(b200l_ctx *c) {
     int cs = 1, cs_shift = 0;
     while (cs * G < ld) { cs *= 2; ++cs_shift; }
     if (cs > MAX_CS) return fail("internal: slice width %d > %d", cs, MAX_CS);
-    // (decided again below, once the message width is known)
     const int direct_pre = (!trans && nrg == 1 && cs * (es / 4) >= 4 && !(c->dbg & 128)) ? 1 : 0;
     const int slot_bytes = trans ? (int)round_up((int64_t)TJ * BX * es, 128) : (int)round_up((int64_t)TR * rowbytes, 128);
     const int rows_pad = trans ? (int)round_up(BX, 8) : (int)round_up(std::max(rows_max, 1), std::max(TR, 8));
@@ -2297,14 +2543,14 @@ static int plan_geometry(b200l_ctx *c) {
         const int o_redT = take(trans ? nt_t * TJ * es : (direct_pre ? ld * es : nrg * 2 * ld * es));
         const int o_red2 = take(trans ? nparts * BX * es : 16);
         const int o_delta = o_redT;
-        const int o_colsum = take(2 * (4 + MAX_CS) * 16);         // gathered scalars + columns (+ group sums)
+        const int o_red = take(NTC * 16);                          // gather partials per thread
         const int o_small = take((2 * MAX_CS + 2 * NW) * 8);      // l1s, es, lsred
         const int o_qpart = take(rows_pad * 8);
         const int o_tilecnt = take(128 * 4);
         if (out) {
             out->off_bar = o_bar; out->off_ctl = o_ctl; out->off_rloc = o_rloc; out->off_qloc = o_qloc;
             out->off_rT = o_rT; out->off_qT = o_qT; out->off_delta = o_delta; out->off_redT = o_redT;
-            out->off_colsum = o_colsum; out->off_small = o_small; out->off_qpart = o_qpart;
+            out->off_red = o_red; out->off_small = o_small; out->off_qpart = o_qpart;
             out->off_red2 = o_red2; out->off_tilecnt = o_tilecnt;
             // multi-GPU send side: the sender warp sends the rows of a pass-2 tile when the
             // consumer warps are done with it (row-major, up to 128 tiles); otherwise the lane that
@@ -2332,30 +2578,26 @@ static int plan_geometry(b200l_ctx *c) {
     c->grid = G;
     c->cpt = cpt;
     c->nt_max = nt_max;
-    // exchange geometry; both exchange fetches land in one ring slot
+    // exchange geometry
     const int wpc = es / 4;
-    // publishing from registers needs complete column sums per thread (one row group) and a
-    // column group inside one message
-    const int direct = trans ? 1 : ((nrg == 1 && cs * wpc >= 4 && !(c->dbg & 128)) ? 1 : 0);
-    // message = 4 scalars + cs columns + 1..4 padding words, 2 (mod 4) words long: even for the
-    // 256-bit stores of the register publish, and with an odd half so that the pair-wise reads
-    // of the gather are free of bank conflicts
-    int mw = 4 + cs * wpc + 1;
-    while (mw % 4 != 2) ++mw;
-    const int slot_words = slot_bytes / 16;
-    int gc = G;
-    if (G * mw > slot_words) {
-        gc = slot_words / mw;
-        if (gc >= 32) gc &= ~31;
-        if (gc < 1) return fail("internal: a ring slot (%d B) cannot hold one exchange message (%d B)",
-                                slot_bytes, mw * 16);
-    }
+    // message = the cs columns of one reader, cs * wpc words: a power of two that divides NTC
+    // (thread = word in the gather).  Publishing from registers needs complete column sums per
+    // thread (one row group) and a column group (4 words, two 256-bit stores) inside one message
+    const int mw = cs * wpc;
+    int mw_shift = 0;
+    while ((1 << mw_shift) < mw) ++mw_shift;
+    if ((1 << mw_shift) != mw || mw > NTC) return fail("internal: message width %d", mw);
+    const int direct = trans ? 1 : ((nrg == 1 && mw >= 4 && !(c->dbg & 128)) ? 1 : 0);
     const int nown = (ld + cs - 1) / cs;                 // CTAs that own at least one column
-    const int dchunk = std::min(ld + (G - nown), slot_words);
     g.TR = TR; g.S = S; g.slot_bytes = slot_bytes; g.cs = cs; g.cs_shift = cs_shift;
     g.ring_bytes = S * slot_bytes;
     g.nrg = nrg; g.ncg = ncg; g.rows_pad = rows_pad; g.rows_max_ = rows_max;
-    g.mw = mw; g.gc = gc; g.dchunk = dchunk; g.nown = nown; g.direct_pub = direct;
+    g.mw = mw; g.mw_shift = mw_shift; g.nown = nown; g.direct_pub = direct;
+    // the step D: fp32 packs two columns per word when a CTA owns at least four (a whole 32-byte sector
+    // per store); a sector then holds 2 * dpw columns of ONE owner CTA
+    g.dpw = (es == 4 && cs >= 4) ? 2 : 1;
+    g.dsec = cs >= 2 * g.dpw ? 1 : 0;
+    g.ackbase = (int)round_up(ld / g.dpw, 2);
     g.BX = BX; g.BXV = BXV; g.TJ = TJ; g.nparts = nparts; g.nt_t = nt_t;
     c->tmap_valid = 0;
     g.inflight = c->max_inflight > 0 ? std::min(c->max_inflight, S) : S;
@@ -2363,8 +2605,13 @@ static int plan_geometry(b200l_ctx *c) {
     // one fit in L2 together; for larger blocks the prefetched lines would be evicted before use
     const int64_t block_bytes = (int64_t)c->brows * c->ld * es;
     g.l2_ahead = ((c->dbg & 8) || 2 * block_bytes > (int64_t)c->l2_bytes * 3 / 4) ? 0 : 1;
-    g.l2_pass = (c->dbg & 16) ? 1 : 0;
-    g.gate_mode = ((c->dbg >> 5) & 3) == 0 ? 2 : (((c->dbg >> 5) & 3) == 3 ? 0 : ((c->dbg >> 5) & 3) == 2 ? 3 : 1);
+    // when the producer may start re-streaming the slab for pass 2, so that the tiles are staged in
+    // the ring while the rest of the exchange runs: 2 = once this CTA's gather is complete (default;
+    // measured on C2: 810 sweeps/s), 1 = once it has published its partial gradient (788), 0 = at once
+    // (the gather's loads queue behind the tiles on the L2 link: 660-700), 3 = after the prox
+    // (diagnostics: dbg bits 5-6 = 1 / 2 / 3 select modes 0 / 1 / 3)
+    const int gm = (c->dbg >> 5) & 3;
+    g.gate_mode = gm == 0 ? 2 : (gm == 1 ? 0 : (gm == 2 ? 1 : 3));
 
     // inboxes of the partial block gradients: [G readers][G writers][cs][WPC] LL words
     const size_t need = (size_t)G * G * mw * 16;
@@ -2381,7 +2628,7 @@ static int plan_geometry(b200l_ctx *c) {
         if (!fn) return fail("internal: no kernel for cpt=%d", cpt);
         CK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_bytes));
         int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, full ? NTHREADS_MG : NTHREADS,
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, NTHREADS,
                                                          c->smem_bytes));
         if (occ < 1) return fail("fused kernel does not fit on an SM (smem=%d)", c->smem_bytes);
     }
@@ -2397,7 +2644,7 @@ extern "C" int b200l_run_config(b200l_ctx *c, int32_t *grid, int32_t *threads, i
     if (need_A(c)) return 1;
     if (plan_geometry(c)) return 1;
     if (grid) *grid = c->grid;
-    if (threads) *threads = c->world > 1 ? NTHREADS_MG : NTHREADS;
+    if (threads) *threads = NTHREADS;
     if (smem_bytes) *smem_bytes = c->smem_bytes;
     if (tile_rows) *tile_rows = c->geo.TR;
     if (ring_slots) *ring_slots = c->geo.S;
@@ -2438,7 +2685,8 @@ static int launch_fused(b200l_ctx *c, const int32_t *order_host, int64_t nsteps,
     // tags tag_base+1 .. tag_base+nsteps+1 are consumed by this launch; never reuse one
     if ((uint64_t)c->tag_base + (uint64_t)nsteps + 2 >= 0xffffffffULL) {
         CK(cudaMemsetAsync(c->gLL, 0, c->gLL_bytes, c->stream));
-        CK(cudaMemsetAsync(c->dLL, 0, (size_t)(c->xld + GMAX) * 16, c->stream));
+        CK(cudaMemsetAsync(c->dLL, 0, (size_t)(c->xld + 2 * GMAX + 2) * 16, c->stream));
+        CK(cudaMemsetAsync(c->sLL, 0, (size_t)GMAX * 4 * 16, c->stream));
         c->tag_base = 0;
     }
 
@@ -2450,7 +2698,7 @@ static int launch_fused(b200l_ctx *c, const int32_t *order_host, int64_t nsteps,
     p.ld = c->layout == B200L_TRANSPOSED ? (int32_t)c->xld : (int32_t)c->ld;
     p.nblocks = c->nblocks;
     p.x = c->x; p.d = c->d; p.drec = c->drec; p.r = c->r;
-    p.gLL = c->gLL; p.dLL = c->dLL; p.abort_flag = c->abort_flag;
+    p.gLL = c->gLL; p.dLL = c->dLL; p.sLL = c->sLL; p.abort_flag = c->abort_flag;
     p.order = order_host ? c->order : nullptr;
     p.nsteps = nsteps;
     p.step0 = c->step_counter;
@@ -2473,11 +2721,16 @@ static int launch_fused(b200l_ctx *c, const int32_t *order_host, int64_t nsteps,
     for (int r = 0; r < B200L_MAX_WORLD; ++r) p.peer[r] = c->peer[r];
     p.dbg = c->dbg;
 
+    if (c->world > 1)
+        for (int r = 0; r < c->world; ++r)
+            if (!c->peer[r])
+                return fail("multi-GPU run: the inbox of rank %d is not mapped (b200l_comm_connect has not "
+                            "completed on this context)", r);
     if (c->layout == B200L_TRANSPOSED && !c->tmap_valid && make_tensor_map(c)) return 1;
     fused_fn fn = ctx_kernel(c, c->world > 1 || trace_dev != nullptr || ttrace_dev != nullptr || (c->dbg & 7) != 0);
     void *args[] = {(void *)&p, (void *)&c->tmap};
     if (timed) CK(cudaEventRecord(c->ev0, c->stream));
-    CK(cudaLaunchCooperativeKernel((const void *)fn, dim3(c->grid), dim3(c->world > 1 ? NTHREADS_MG : NTHREADS), args,
+    CK(cudaLaunchCooperativeKernel((const void *)fn, dim3(c->grid), dim3(NTHREADS), args,
                                    (size_t)c->smem_bytes, c->stream));
     if (timed) CK(cudaEventRecord(c->ev1, c->stream));
     c->step_counter += nsteps;
@@ -2595,16 +2848,27 @@ extern "C" int b200l_debug_flags(b200l_ctx *c, int32_t flags) {
 // ------------------------------------------------------------------------------------
 // multi-GPU: one process per GPU, column slice `rank` of every block per rank
 // ------------------------------------------------------------------------------------
-static int comm_release(b200l_ctx *c) {
+// Teardown in two steps, with a barrier over the ranks between them (distributed.disconnect):
+// first every rank closes the peers' inboxes it had mapped, then it frees its own -- freeing an
+// exported allocation that an importer still has open is undefined behaviour.
+static int comm_close_peers(b200l_ctx *c) {
     for (int r = 0; r < B200L_MAX_WORLD; ++r) {
-        if (!c->peer[r]) continue;
-        if (r == c->rank) cudaFree(c->peer[r]);
-        else cudaIpcCloseMemHandle(c->peer[r]);
+        if (!c->peer[r] || r == c->rank) continue;
+        if (c->peer_ipc) cudaIpcCloseMemHandle(c->peer[r]);
         c->peer[r] = nullptr;
     }
+    return 0;
+}
+
+static int comm_release(b200l_ctx *c) {
+    comm_close_peers(c);
+    if (c->world > 1 && c->peer[c->rank] && c->peer_ipc) cudaFree(c->peer[c->rank]);
+    for (int r = 0; r < B200L_MAX_WORLD; ++r) c->peer[r] = nullptr;
     c->world = 1;
     c->rank = 0;
     c->inbox_bytes = 0;
+    c->peer_ipc = 0;
+    c->mc = nullptr;
     c->geo_valid = 0;
     return 0;
 }
@@ -2634,6 +2898,7 @@ extern "C" int b200l_comm_export(b200l_ctx *c, int32_t rank, int32_t world, void
     c->rank = rank;
     c->peer[rank] = buf;
     c->inbox_bytes = bytes;
+    c->peer_ipc = 1;
     return 0;
 }
 
@@ -2647,9 +2912,59 @@ extern "C" int b200l_comm_connect(b200l_ctx *c, const void *all_handles, int32_t
         cudaIpcMemHandle_t h;
         memcpy(&h, (const char *)all_handles + (size_t)r * handle_stride, sizeof(h));
         void *ptr = nullptr;
-        CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            comm_close_peers(c);      // what was mapped so far; the run refuses to start without all peers
+            return fail("cudaIpcOpenMemHandle for rank %d failed: %s", r, cudaGetErrorString(e));
+        }
         c->peer[r] = (ulonglong2 *)ptr;
     }
+    return 0;
+}
+
+// first half of the teardown: unmap the peers' inboxes (collective: every rank, then a barrier,
+// then b200l_comm_destroy)
+extern "C" int b200l_comm_close_peers(b200l_ctx *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    return comm_close_peers(c);
+}
+
+// number of words (16 bytes each) of one rank's inbox for the current shape and world size
+extern "C" int b200l_comm_inbox_bytes(b200l_ctx *c, int32_t world, int64_t *bytes) {
+    if (need_A(c) || !bytes) return c ? fail("bytes is NULL") : 1;
+    if (world < 2 || world > B200L_MAX_WORLD) return fail("world must be 2..%d", B200L_MAX_WORLD);
+    const int w0 = c->world, r0 = c->rank;
+    c->world = world; c->geo_valid = 0;
+    const int rc = plan_geometry(c);
+    const size_t qw = (size_t)round_up(c->geo.rows_max_ + 2, 2);
+    *bytes = rc ? 0 : (int64_t)(2 * (size_t)c->grid * world * qw * 16);
+    c->world = w0; c->rank = r0; c->geo_valid = 0;
+    return rc;
+}
+
+// inboxes allocated and mapped by the caller (e.g. torch symmetric memory): peer_ptrs[r] is the
+// address, in THIS process, of rank r's inbox (b200l_comm_inbox_bytes bytes each, zero-filled);
+// mc_ptr, when not NULL, is a multicast (NVLS) mapping of the same buffers: one multimem store
+// then reaches every rank's inbox.  The caller keeps ownership of the memory.
+extern "C" int b200l_comm_attach(b200l_ctx *c, int32_t rank, int32_t world, void *const *peer_ptrs, void *mc_ptr) {
+    if (!c || !peer_ptrs) return fail("NULL argument");
+    if (world < 2 || world > B200L_MAX_WORLD) return fail("world must be 2..%d", B200L_MAX_WORLD);
+    if (rank < 0 || rank >= world) return fail("rank %d out of range", rank);
+    CK(cudaSetDevice(c->device));
+    comm_release(c);
+    for (int r = 0; r < world; ++r)
+        if (!peer_ptrs[r]) return fail("peer_ptrs[%d] is NULL", r);
+    c->world = world;
+    c->rank = rank;
+    c->geo_valid = 0;
+    if (plan_geometry(c)) { c->world = 1; c->rank = 0; c->geo_valid = 0; return 1; }
+    for (int r = 0; r < world; ++r) c->peer[r] = (ulonglong2 *)peer_ptrs[r];
+    c->mc = (ulonglong2 *)mc_ptr;
+    c->peer_ipc = 0;
+    const size_t qw = (size_t)round_up(c->geo.rows_max_ + 2, 2);
+    c->inbox_bytes = 2 * (size_t)c->grid * world * qw * 16;
     return 0;
 }
 

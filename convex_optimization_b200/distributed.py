@@ -99,6 +99,10 @@ def connect(gpu_cal, group=None):
 
 
 def disconnect(gpu_cal, group=None):
+    """collective teardown: every rank unmaps the peers' inboxes, and only when all have done so
+    does a rank free its own (an exported allocation must outlive its importers' mappings)"""
     dist = _dist()
-    dist.barrier(group=group)
+    dist.barrier(group=group)                                        # nobody is still running a solve
+    _lib.check(gpu_cal._lib.b200l_comm_close_peers(gpu_cal.ctx))
+    dist.barrier(group=group)                                        # every mapping of my inbox is closed
     _lib.check(gpu_cal._lib.b200l_comm_destroy(gpu_cal.ctx))

@@ -18,6 +18,62 @@ import numpy as np
 from . import _lib
 
 
+class DeviceBlock:
+    """``gpu_cal.A_b_gpu[m]``: column block m on the device, presented the way the reference's
+    solver classes reach through it (lasso.py:336,349-351,546): ``.shape == (N, w)`` and
+    ``.gpudata`` (an int device address).  The address also carries what a bare pointer cannot
+    say -- the padded leading dimension, the storage type / layout and the owning
+    ``GPU_Calculation`` -- so the ``skcuda.cublas`` shim can run a ``cublasDgemv`` on this
+    block with the library's own kernels.  ``.tensor`` is the torch view, ``.get()`` a host copy."""
+
+    def __init__(self, gpu_cal, m):
+        self._cal = gpu_cal
+        self._m = int(m)
+        self.shape = (gpu_cal.MAT_HEIGHT, gpu_cal.MAT_WIDTH)
+        self.dtype = np.dtype(np.float64 if gpu_cal.TYPE == 'double' else np.float32)
+        self.size = self.shape[0] * self.shape[1]
+
+    @property
+    def tensor(self):
+        cal = self._cal
+        store = cal._A_store[self._m]
+        if cal.LAYOUT == 'row':
+            return store[:, :cal.MAT_WIDTH]
+        return store[:, :cal.MAT_HEIGHT].t()
+
+    @property
+    def gpudata(self):
+        from .dropin.pycuda.gpuarray import DevicePointer
+        cal = self._cal
+        return DevicePointer.wrap(cal._A_store[self._m].data_ptr(), cal._A_store, ld=cal.ld,
+                                  block=(cal, self._m))
+
+    def get(self):
+        return self.tensor.cpu().numpy()
+
+    def cpu(self):
+        return self.tensor.cpu()
+
+
+class DeviceBlocks:
+    """sequence of ``DeviceBlock`` (the reference's ``A_b_gpu``, gpu_calculation.py:224)"""
+
+    def __init__(self, gpu_cal):
+        self._cal = gpu_cal
+
+    def __len__(self):
+        return self._cal.Block
+
+    def __getitem__(self, m):
+        if not -self._cal.Block <= m < self._cal.Block:
+            raise IndexError(m)
+        return DeviceBlock(self._cal, m % self._cal.Block)
+
+    @property
+    def shape(self):
+        return (self._cal.Block, self._cal.MAT_HEIGHT, self._cal.MAT_WIDTH)
+
+
 class GPU_Calculation:
     # launch-shape knobs of the reference kernels (gpu_calculation.py:143-145).  They are
     # accepted and stored so drivers that set them (cpu_vs_gpu.py:104-105) run unchanged;
@@ -110,11 +166,8 @@ class GPU_Calculation:
     def _adopt(self, store):
         N, w = self.MAT_HEIGHT, self.MAT_WIDTH
         self._A_store = store
-        # the reference exposes A_b_gpu[m] with shape (N, w) (lasso.py:336,349)
-        if self.LAYOUT == 'row':
-            self.A_b_gpu = store[:, :, :w]
-        else:
-            self.A_b_gpu = store[:, :, :N].transpose(1, 2)
+        # the reference exposes A_b_gpu[m] with shape (N, w) and .gpudata (lasso.py:336,349)
+        self.A_b_gpu = DeviceBlocks(self)
         _lib.check(self._lib.b200l_ctx_bind_A(self.ctx, ctypes.c_void_p(store.data_ptr())))
 
     def __del__(self):

@@ -76,6 +76,16 @@ int b200l_ctx_bind_A(b200l_ctx *ctx, const void *A_dev);
 int b200l_diag_ata(b200l_ctx *ctx, double *out_host);
 int b200l_gemv_t(b200l_ctx *ctx, int32_t m, const double *r_host, double *g_host);
 int b200l_gemv_n(b200l_ctx *ctx, int32_t m, const double *d_host, double *q_host);
+/* The same two mat-vecs on DEVICE vectors of doubles, queued on the context's stream without any
+ * copy to or from the host and without synchronisation: what the reference's cuBLAS classes do
+ * with cublasDgemv on gpuarrays (lasso.py:334-353, :404-419, :546-557).  r_dev: N entries,
+ * g_dev: w entries; d_dev: w entries, q_dev: N entries. */
+int b200l_gemv_t_dev(b200l_ctx *ctx, int32_t m, const double *r_dev, double *g_dev);
+int b200l_gemv_n_dev(b200l_ctx *ctx, int32_t m, const double *d_dev, double *q_dev);
+/* diag(A^T A) is computed once per bound matrix (one pass over A) and kept: b200l_diag_ata and
+ * b200l_set_problem share it.  b200l_set_diag replaces it by the caller's values -- the d_ATA
+ * argument of the solver classes (lasso.py:26-30), d_host[nblocks * w] doubles, block-major. */
+int b200l_set_diag(b200l_ctx *ctx, const double *d_host);
 
 /* -- fused solver state -------------------------------------------------------------
  * The fused path keeps x (K), the running residual r = A x - b (N), d = diag(A^T A) and
@@ -180,9 +190,25 @@ int b200l_scale_rows(b200l_ctx *ctx, const double *scale_host);
 int b200l_comm_export(b200l_ctx *ctx, int32_t rank, int32_t world, void *handle_out, int32_t handle_bytes);
 int b200l_comm_connect(b200l_ctx *ctx, const void *all_handles, int32_t handle_stride);
 int b200l_comm_destroy(b200l_ctx *ctx);
+/* Teardown is collective and has two halves: every rank calls comm_close_peers (unmaps the
+ * peers' inboxes), then a barrier over the ranks, then comm_destroy (frees its own inbox): an
+ * exported allocation must not be freed while an importer still has it open. */
+int b200l_comm_close_peers(b200l_ctx *ctx);
+/* Inboxes provided by the caller instead of CUDA IPC (e.g. symmetric memory of the host
+ * framework): comm_inbox_bytes gives the size one rank's inbox needs for this shape and world
+ * size; comm_attach takes the addresses, in this process, of all ranks' inboxes (zero-filled,
+ * peer_ptrs[rank] local) and, when not NULL, a multicast (NVLS) mapping of the same buffers --
+ * the kernel then sends every row with ONE multimem store instead of world-1 peer stores.  The
+ * caller keeps ownership of the memory; comm_destroy only forgets it. */
+int b200l_comm_inbox_bytes(b200l_ctx *ctx, int32_t world, int64_t *bytes);
+int b200l_comm_attach(b200l_ctx *ctx, int32_t rank, int32_t world, void *const *peer_ptrs, void *mc_ptr);
 
 /* 0.5*|r|^2 + mu*|x|_1 from the device state (lasso.py:46-47 with the running residual) */
 int b200l_objective(b200l_ctx *ctx, double mu, double *value);
+/* the two terms separately: rss = |r|^2 and l1 = |x|_1 of THIS context.  With column shards on
+ * several GPUs r is replicated but x is the local slice: the objective of the whole instance is
+ * 0.5 * rss + mu * (sum of l1 over the ranks). */
+int b200l_objective_terms(b200l_ctx *ctx, double *rss, double *l1);
 
 #ifdef __cplusplus
 }

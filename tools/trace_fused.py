@@ -92,8 +92,16 @@ def main():
             _lib.check(lib.b200l_run(ctx, None, BLOCK, float(mu), -1.0, None, None, None, None,
                                      ctypes.byref(k2)))
             ts.append(k2.value)
-        t = tr.astype(np.float64)[:, :, :10] * 1e-3          # us
+        # stamps are SM cycles since the CTA's start; every CTA carries a (globaltimer, cycle) pair
+        # at both ends of the launch (slots 13 / 14 of the first and the last step)
+        trf = tr.astype(np.float64)
+        ns_per_cycle = (trf[:, -1, 13] - trf[:, 0, 13]) / trf[:, -1, 11]
+        scale = (ns_per_cycle * 1e-3)[:, None, None]         # us per cycle, per CTA
+        g0 = (trf[:, 0, 13] - trf[:, 0, 13].min()) * 1e-3    # start of the CTA on the common clock, us
+        t = trf[:, :, :10] * scale
+        t_abs = t + g0[:, None, None]
         s = t[:, BLOCK:, :]                        # skip the first sweep of the launch
+        s_abs = t_abs[:, BLOCK:, :]
         dur = np.diff(s, axis=2)
         step_len = s[:, 1:, 0] - s[:, :-1, 0]
         out = {"tuning": {"slot_bytes": slot, "inflight": infl, "dbg": dbg}, "geo": geo,
@@ -105,24 +113,25 @@ def main():
                "phases_us_mean_over_ctas": {n: round(float(dur[:, :, i].mean()), 3) for i, n in enumerate(PHASES)},
                "phases_us_max_cta": {n: round(float(dur[:, :, i].mean(axis=1).max()), 3) for i, n in enumerate(PHASES)},
                "phases_us_min_cta": {n: round(float(dur[:, :, i].mean(axis=1).min()), 3) for i, n in enumerate(PHASES)},
-               "skew_us_pass1_end": float((s[:, :, 1].max(axis=0) - s[:, :, 1].min(axis=0)).mean()),
-               "skew_us_step_start": float((s[:, :, 0].max(axis=0) - s[:, :, 0].min(axis=0)).mean())}
-        if NT >= 15:        # inside "gather g": fetch landed, tags checked, barrier, column sums (last fetch)
-            f = tr.astype(np.float64)[:, BLOCK:, :] * 1e-3
+               "sm_mhz_from_trace": float(1e3 / np.median(ns_per_cycle)),
+               "skew_us_pass1_end": float((s_abs[:, :, 1].max(axis=0) - s_abs[:, :, 1].min(axis=0)).mean()),
+               "skew_us_step_start": float((s_abs[:, :, 0].max(axis=0) - s_abs[:, :, 0].min(axis=0)).mean())}
+        if NT >= 15:        # inside "gather g": every word valid, combined over the threads, final sums
+            f = trf[:, BLOCK:, :] * scale
             out["gather_g_detail_us"] = {
-                "publish end -> inbox fetch landed": round(float((f[:, :, 10] - f[:, :, 2]).mean()), 3),
-                "tags checked, missing words repaired from L2": round(float((f[:, :, 12] - f[:, :, 10]).mean()), 3),
-                "barrier": round(float((f[:, :, 13] - f[:, :, 12]).mean()), 3),
-                "column sums": round(float((f[:, :, 14] - f[:, :, 13]).mean()), 3),
-                "closing barrier": round(float((f[:, :, 3] - f[:, :, 14]).mean()), 3),
-                "words repaired per thread and step": round(float(tr[:, BLOCK:, 11].mean()), 3)}
+                "publish end -> every word of this thread valid (L2 loads + polls)": round(float((f[:, :, 10] - f[:, :, 2]).mean()), 3),
+                "shuffle tree + barrier": round(float((f[:, :, 12] - f[:, :, 10]).mean()), 3),
+                "sums over the warps": round(float((f[:, :, 3] - f[:, :, 12]).mean()), 3),
+                "words polled again per thread and step (thread 0)": round(float(tr[:, BLOCK:-1, 11].mean()), 3)}
+            out["gather D end -> pass-2 loop entered (r update, l1/err terms, D to registers)"] = \
+                round(float((f[:, :, 14] - f[:, :, 7]).mean()), 3)
         if world > 1 and NT >= 16:
-            f = tr.astype(np.float64)[:, BLOCK:, :] * 1e-3
+            f = trf[:, BLOCK:, :] * scale
             out["peer_rows_us"] = {
                 "pass 2 end -> all peer rows summed (collector warp)": round(float((f[:, :, 15] - f[:, :, 8]).mean()), 3),
                 "max over CTAs": round(float((f[:, :, 15] - f[:, :, 8]).max(axis=0).mean()), 3)}
         if args.tiles:
-            ft = tt.astype(np.float64)[:, BLOCK:, :] * 1e-3
+            ft = tt.astype(np.float64)[:, BLOCK:, :] * scale
             ntile = min(16, geo["tiles_per_slab"])
             out["tiles_us"] = {
                 "pass1 tile (data landed -> done, incl. wait for peer rows)":
@@ -131,12 +140,17 @@ def main():
                     [round(float((ft[:, :, t + 1] - ft[:, :, 16 + t]).mean()), 3) for t in range(ntile - 1)],
                 "pass2 tile": [round(float((ft[:, :, 48 + t] - ft[:, :, 32 + t]).mean()), 3) for t in range(ntile)]}
             # the tile stamps are absolute, the phase stamps relative to the kernel start of the CTA
-            fp = tr.astype(np.float64)[:, BLOCK:, :] * 1e-3
+            fp = trf[:, BLOCK:, :] * scale
             off = ft[:, :, 16 + ntile - 1] - fp[:, :, 1]
             out["tiles_us"]["pass2 tile 0 issued by the producer, after the end of gather g"] = \
                 round(float((ft[:, :, 80] - off - fp[:, :, 3]).mean()), 3)
             out["tiles_us"]["pass2 tile 0 landed, after the end of gather D"] = \
                 round(float((ft[:, :, 32] - off - fp[:, :, 7]).mean()), 3)
+            if dbg & 512:
+                out["tiles_us"]["pass2 tile 0 really landed (producer polls), after its issue"] = \
+                    round(float((ft[:, :, 95] - ft[:, :, 80]).mean()), 3)
+                out["tiles_us"]["pass2 tile 0 really landed, after the end of gather D"] = \
+                    round(float((ft[:, :, 95] - off - fp[:, :, 7]).mean()), 3)
             out["tiles_us"]["pass2 tile 0 landed, after its issue"] = round(float((ft[:, :, 32] - ft[:, :, 80]).mean()), 3)
             out["tiles_us"]["pass2 tile end -> next tile start"] = \
                 [round(float((ft[:, :, 32 + t + 1] - ft[:, :, 48 + t]).mean()), 3) for t in range(ntile - 1)]
@@ -147,9 +161,9 @@ def main():
         if world > 1:
             out["rank"] = rank
         if rank == 0 or args.all_ranks:
-            print(json.dumps({k: out[k] for k in ("tuning", "ms_per_sweep", "sweeps_per_s", "us_per_block_step", "us_per_block_step_by_sweep",
+            print(json.dumps({k: out[k] for k in ("tuning", "ms_per_sweep", "ms_per_sweep_traced", "sweeps_per_s", "us_per_block_step", "us_per_block_step_by_sweep", "sm_mhz_from_trace",
                                                    "phases_us_mean_over_ctas", "skew_us_pass1_end",
-                                                   "gather_g_detail_us", "peer_rows_us", "tiles_us", "rank") if k in out}))
+                                                   "gather_g_detail_us", "gather D end -> pass-2 loop entered (r update, l1/err terms, D to registers)", "peer_rows_us", "tiles_us", "rank") if k in out}))
         sys.stdout.flush()
     out = results if len(results) > 1 else results[0]
     if world > 1:
