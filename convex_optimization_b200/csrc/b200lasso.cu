@@ -66,7 +66,7 @@ constexpr int NTC = NW * 32;           // consumer threads
 // (setmaxnreg), whose inner loops want many loads in flight.
 constexpr int NTHREADS = NTC + 128;
 constexpr int HELPER_REGS = 56, CONSUMER_REGS = 224;            // 256 * 224 + 128 * 56 = 64512 = 384 * 168
-constexpr int HELPER_REGS_FULL = 96, CONSUMER_REGS_FULL = 200;  // (the collector warp keeps 14 words in flight)
+constexpr int HELPER_REGS_MG = 152, CONSUMER_REGS_MG = 176;    // (the collector warp keeps up to 21 words per lane in flight)
 constexpr int MAX_CS = 64;             // max stage-2 slice width (columns per CTA)
 
 template <typename T> struct VT;
@@ -222,6 +222,14 @@ __device__ __forceinline__ double ll_dbl(const ulonglong2 v) {
 __device__ __forceinline__ void ll_st_dbl(ulonglong2 *p, double a, uint32_t tag) {
     ll_st(p, ll_pack((uint32_t)__double2loint(a), tag), ll_pack((uint32_t)__double2hiint(a), tag));
 }
+// the same word through a multicast (NVLS) mapping: ONE store, delivered by the switch to the
+// replica of every GPU bound to the multicast object (SASS: a multimem store)
+__device__ __forceinline__ void mm_st_dbl(ulonglong2 *p, double a, uint32_t tag) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p),
+                 "f"(__int_as_float(__double2loint(a))), "f"(__uint_as_float(tag)),
+                 "f"(__int_as_float(__double2hiint(a))), "f"(__uint_as_float(tag))
+                 : "memory");
+}
 
 // per-type encoding of the exchanged values: (g_r, g_q) of a column as two floats in one
 // word or one word per double; the step D as one 8-byte word per float or one 16-byte word
@@ -340,6 +348,7 @@ struct RunParams {
     int32_t xmode;            // multi-GPU send side: 0 the sender warp sends finished pass-2 tiles, 1 the lane that finishes a row sends it
     int32_t world, rank, qw, tile_sends; // qw: words per rank in a cell; tile_sends: plan for xmode 0
     ulonglong2 *peer[B200L_MAX_WORLD];
+    ulonglong2 *mc;           // multicast mapping of all ranks' inboxes (NVLS) or NULL
     int32_t direct_pub;       // partial gradients are published from registers (one row group)
     int32_t gate_mode;        // 0: re-stream freely, 1/2/3: after inbox fetch issued / gather done / D fetch issued
     // transposed layout: a tile is TJ block columns x BX residual entries of this CTA
@@ -481,10 +490,11 @@ __device__ __forceinline__ T warp_sum_pair(const T a, const T b, const int lane)
 //       block is then a 2-D box (all columns x its residual entries), fetched tile by tile
 //       through a tensor map.  Pass 1 is a row-dot per column (thread = column), pass 2 an
 //       axpy over columns (thread = (16-byte group of residual entries, column part)).
-// FULL : with the multi-GPU exchange, the phase / tile tracing and the diagnostic switches.  The
-//       plain single-GPU solve runs the FULL = false instantiation: the per-step code has to
-//       stay resident in the instruction cache and every rarely used branch costs footprint.
-template <typename T, int CPT, bool TRANS, bool FULL>
+// MODE : 0 = the plain single-GPU solve, 1 = with the multi-GPU exchange (sender / collector warps),
+//       2 = 1 + the phase / tile tracing and the diagnostic switches.  Three instantiations because
+//       the per-step code has to stay resident in the instruction cache and every rarely used
+//       branch costs footprint (and registers in the inner loops).
+template <typename T, int CPT, bool TRANS, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, const __grid_constant__ CUtensorMap tmap) {
     using VecT = typename VT<T>::type;
     using LL = LLW<T>;
@@ -493,7 +503,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
     constexpr int V = VT<T>::V;
     constexpr int WPC = LL::WPC;
     constexpr int DK = CPT == 1 ? NTC / 32 : 0;
-    const int WORLD = FULL ? p.world : 1, DBG = FULL ? p.dbg : 0;
+    constexpr bool MG = MODE >= 1, DIAG = MODE == 2;
+    const int WORLD = MG ? p.world : 1, DBG = DIAG ? p.dbg : 0;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *ring = smem;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + p.off_bar);
@@ -558,7 +569,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
     // register re-balancing between the warpgroups: every warp of a warpgroup executes it, first
     // thing in its role branch (the allocator sizes each branch by the limit set inside it)
     if (wid >= NW) {
-        if (FULL) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HELPER_REGS_FULL));
+        if (MG) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HELPER_REGS_MG));
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HELPER_REGS));
     if (wid == NW) {
         // ============================ producer warp ================================
@@ -622,7 +633,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                             // (from L2), pull the slab of the next step into L2
                             if (pass == 1 && An) tma_prefetch_l2(An + (size_t)t * tile_bytes, bytes);
                         }
-                        if (FULL && p.ttrace && t < 16)
+                        if (DIAG && p.ttrace && t < 16 && WORLD == 1)
                             p.ttrace[((size_t)c * p.nsteps + step) * NTTRACE + 64 + pass * 16 + t] = tstamp();
                         cur.advance(S);
                         ++k;
@@ -657,9 +668,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                 __threadfence_block();
                 if (lane < 2) {                // l1 and err terms of my columns (set before pass 2)
                     const double v = ctl->sp[2 + lane];
+                    if (p.mc) {
+                        mm_st_dbl(p.mc + mine + rows_c + lane, v, tag);
+                    } else {
 #pragma unroll 1
-                    for (int pr = 0; pr < WORLD; ++pr)
-                        if (pr != p.rank) ll_st_dbl(p.peer[pr] + mine + rows_c + lane, v, tag);
+                        for (int pr = 0; pr < WORLD; ++pr)
+                            if (pr != p.rank) ll_st_dbl(p.peer[pr] + mine + rows_c + lane, v, tag);
+                    }
                 }
 #pragma unroll 1
                 for (int t = 0; t < nt; ++t) {
@@ -673,11 +688,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
 #pragma unroll 1
                     for (int i = lane; i < rows_t; i += 32) {
                         const double v = qpart[t * TR + i];
+                        if (p.mc) {            // one store, the switch delivers it to every rank
+                            mm_st_dbl(p.mc + mine + t * TR + i, v, tag);
+                        } else {
 #pragma unroll 1
-                        for (int pr = 0; pr < WORLD; ++pr)
-                            if (pr != p.rank) ll_st_dbl(p.peer[pr] + mine + t * TR + i, v, tag);
+                            for (int pr = 0; pr < WORLD; ++pr)
+                                if (pr != p.rank) ll_st_dbl(p.peer[pr] + mine + t * TR + i, v, tag);
+                        }
                     }
                     __syncwarp();
+                    if (DIAG && p.ttrace && lane == 0 && t < 16)
+                        p.ttrace[((size_t)c * p.nsteps + hs) * NTTRACE + 64 + t] = tstamp();
                     if (lane == 0) {
                         tilecnt[t & 127] = 0;
                         // my rows of this tile are final: the collector may add them up
@@ -700,12 +721,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
         if (WORLD > 1) {
             Waiter hw{p.abort_flag, &ctl->abort, p.wait_limit_ns, 0u, 0ull, p.state + 4, 0};
             const int nq = rows_c + 2;                       // rows, then the l1 and err terms
+            constexpr int CH = 3;                            // C2 shard: 68 rows + 2 scalars = one batch
             bool live = true;
             for (long long hs = 0; live; ++hs) {
                 const uint32_t tag = p.tag_base + (uint32_t)hs + 1u;
                 const ulonglong2 *mycell = p.peer[p.rank] + (((size_t)(tag & 1u) * G + c) * WORLD) * p.qw;
                 double trq = 0.0, tqq = 0.0;
                 int own_rows = 0;                            // my own rows below this index are final
+                int rel_t = 0;                               // (trace) tiles whose rows have been released
                 unsigned spin = 0;
                 // nothing can arrive before the ranks are in pass 2 of this step: nap until mine
                 // begins (shared-memory flag, no L2 traffic)
@@ -719,11 +742,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                 if (!live) break;
                 hw.begin((hs << 32) | (2LL << 30));
 #pragma unroll 1
-                for (int i0 = 0; i0 < nq && live; i0 += 64) {        // 2 x 32 words x (world-1) sources in flight
-                    ulonglong2 w[2][B200L_MAX_WORLD - 1];
-                    bool done[2];
+                for (int i0 = 0; i0 < nq && live; i0 += 32 * CH) {   // CH x 32 words x (world-1) sources in flight
+                    ulonglong2 w[CH][B200L_MAX_WORLD - 1];
+                    bool done[CH];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
+                    for (int h = 0; h < CH; ++h) {
                         const int i = i0 + 32 * h + lane;
                         done[h] = i >= nq;
 #pragma unroll
@@ -751,7 +774,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                             }
                         }
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
+                        for (int h = 0; h < CH; ++h) {
                             if (!done[h]) {
                                 const int i = i0 + 32 * h + lane;
                                 bool ok = true;
@@ -788,15 +811,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                         }
                         // watchdog every 16th trip (the poll period is the L2 round trip)
                         if (((++spin & 15u) == 0u && !__all_sync(0xffffffffu, hw.again())) || (DBG & 1)) {
-                            done[0] = done[1] = true;        // aborted: the consumers find the abort flag
+#pragma unroll
+                            for (int h = 0; h < CH; ++h) done[h] = true;   // aborted: the consumers find the abort flag
                         }
-                        const unsigned nd0 = __ballot_sync(0xffffffffu, !done[0]);
-                        const unsigned nd1 = __ballot_sync(0xffffffffu, !done[1]);
-                        const int ready = nd0 ? i0 + __ffs(nd0) - 1 : (nd1 ? i0 + 32 + __ffs(nd1) - 1 : i0 + 64);
+                        int ready = i0 + 32 * CH;                // first row of this batch that is not summed yet
+                        bool any = false;
+#pragma unroll
+                        for (int h = CH - 1; h >= 0; --h) {
+                            const unsigned nd = __ballot_sync(0xffffffffu, !done[h]);
+                            if (nd) { ready = i0 + 32 * h + __ffs(nd) - 1; any = true; }
+                        }
                         __threadfence_block();
                         if (lane == 0)
                             *(volatile long long *)&ctl->qready = ((hs + 1) << 32) | (long long)min(ready, rows_c);
-                        if (!(nd0 | nd1)) break;
+                        if (DIAG && p.ttrace && lane == 0) {
+                            const unsigned long long now = tstamp();
+                            for (; rel_t < 16 && rel_t * TR < rows_c && min((rel_t + 1) * TR, rows_c) <= ready; ++rel_t)
+                                p.ttrace[((size_t)c * p.nsteps + hs) * NTTRACE + 80 + rel_t] = now;
+                        }
+                        if (!any) break;
                     }
                 }
                 if (!live) break;
@@ -811,7 +844,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                     __threadfence_block();
                     *(volatile long long *)&ctl->qready = ((hs + 1) << 32) | 0x7fffffffLL;
                     *(volatile long long *)&ctl->sc_go = hs + 1;         // the scalar warp takes them from here
-                    if (p.trace)
+                    if (DIAG && p.trace)
                         p.trace[((size_t)c * p.nsteps + hs) * NTRACE + 15] =
                             tstamp() - *(volatile unsigned long long *)&ctl->t_start;
                 }
@@ -889,7 +922,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
     }
     } else {
         // ============================ consumer warps ===============================
-        if (FULL) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS_FULL));
+        if (MG) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS_MG));
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
         for (int i = tid; i < rows_c; i += NTC) {
             const double rv = p.r[row0 + i];
@@ -916,7 +949,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
         int64_t steps_done = 0;
         const unsigned long long t_start = globaltimer_ns();
         const unsigned long long c_start = tstamp();
-        if (FULL && tid == 0) ctl->t_start = c_start;
+        if (DIAG && tid == 0) ctl->t_start = c_start;
         const int cs = p.cs, nrg = p.nrg;
         const double mu = p.mu;
         const uint32_t tag0 = p.tag_base;
@@ -932,9 +965,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
             __threadfence_block();
         };
         unsigned long long *trace =
-            (FULL && p.trace != nullptr && tid == 0) ? p.trace + (size_t)c * p.nsteps * NTRACE : nullptr;
+            (DIAG && p.trace != nullptr && tid == 0) ? p.trace + (size_t)c * p.nsteps * NTRACE : nullptr;
         unsigned long long *ttrace =
-            (FULL && p.ttrace != nullptr && tid == 0) ? p.ttrace + (size_t)c * p.nsteps * NTTRACE : nullptr;
+            (DIAG && p.ttrace != nullptr && tid == 0) ? p.ttrace + (size_t)c * p.nsteps * NTTRACE : nullptr;
         int mc = (int)(p.step0 % p.nblocks);
 
         // pass-1 mapping: thread = (column group cg0 [+k*NTC], row group rg of nrg)
@@ -1393,9 +1426,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
             const size_t cell = (((size_t)(tag & 1u) * G + c) * WORLD) * p.qw;
             auto send_row = [&](int idx, double v) {
                 if (WORLD > 1) {
+                    if (p.mc) {
+                        mm_st_dbl(p.mc + cell + (size_t)p.rank * p.qw + idx, v, tag);
+                    } else {
 #pragma unroll 1
-                    for (int pr = 0; pr < WORLD; ++pr)
-                        if (pr != p.rank) ll_st_dbl(p.peer[pr] + cell + (size_t)p.rank * p.qw + idx, v, tag);
+                        for (int pr = 0; pr < WORLD; ++pr)
+                            if (pr != p.rank) ll_st_dbl(p.peer[pr] + cell + (size_t)p.rank * p.qw + idx, v, tag);
+                    }
                 }
             };
             if (WORLD > 1 && tid == 0) {   // my l1 / err terms of this step travel with the rows
@@ -1466,6 +1503,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                     }
                 };
                 if (trace) trace[step * NTRACE + 14] = tstamp() - c_start;
+                // multi-GPU: the sender warp sends a tile's rows to the peers when all NW warps have
+                // counted it
+                auto count_tile = [&](int tile_idx) {
+                    if (WORLD > 1 && p.xmode == 0) {
+                        __syncwarp();
+                        if (lane == 0) {
+                            __threadfence_block();
+                            atomicAdd(tilecnt + (tile_idx & 127), 1);
+                        }
+                    }
+                };
                 T pqa = (T)0, pqb = (T)0;
                 int pend_row = -1;
                 bool pend_two = false;
@@ -1491,8 +1539,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                         }
                     } else if (!(DBG & 4)) {
                         // two rows per trip (the odd last row is paired with itself).  The shuffle tree
-                        // of a pair is a chain of dependent instructions: it runs one trip late, under
-                        // the loads of the next pair (multi-GPU: at once, the peers wait for the rows)
+                        // of a pair is a chain of dependent instructions: it runs one trip late, in
+                        // front of the loads of the next pair (multi-GPU: at once, the sender warp waits
+                        // for the rows; deferring there was measured slower)
 #pragma unroll 1
                         for (int rr = wid; rr < rows_t; rr += 2 * NW) {
                             const bool two = rr + NW < rows_t;
@@ -1508,15 +1557,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                                 flush_pair(t * TR + rr, two, qa, qb);
                             }
                         }
-                        if (WORLD > 1 && p.xmode == 0) {
-                            // multi-GPU: count the warps that are done with this tile; the sender
-                            // warp sends the tile's rows to the peers when all are
-                            __syncwarp();
-                            if (lane == 0) {
-                                __threadfence_block();
-                                atomicAdd(tilecnt + (t2 & 127), 1);
-                            }
-                        }
+                        count_tile(t2);
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(empty + slot);
@@ -2411,7 +2452,10 @@ extern "C" int b200l_objective_terms(b200l_ctx *c, double *rss, double *l1) {
 // the one computed from the bound matrix: d (nblocks, w) doubles, 1/d taken like lasso.py:29-30
 extern "C" int b200l_set_diag(b200l_ctx *c, const double *d_host) {
     if (need_A(c)) return 1;
-    if (!d_host) return fail("d_host is NULL");
+    if (!d_host) {                      // back to the diagonal of the bound matrix (recomputed when next needed)
+        c->have_diag = 0;
+        return 0;
+    }
     const int64_t nx = (int64_t)c->nblocks * c->xld;
     CK(cudaMemsetAsync(c->dsum, 0, (size_t)nx * 8, c->stream));
     CK(cudaMemcpy2DAsync(c->dsum, (size_t)c->xld * 8, d_host, (size_t)c->w * 8, (size_t)c->w * 8,
@@ -2436,24 +2480,25 @@ extern "C" int b200l_set_tuning(b200l_ctx *c, int32_t slot_bytes_target, int32_t
 
 typedef void (*fused_fn)(const RunParams, const CUtensorMap);
 
-template <typename T, bool FULL>
+template <typename T, int MODE>
 static fused_fn pick_kernel(int cpt, bool trans) {
-    if (trans) return lasso_fused<T, 1, true, FULL>;
+    if (trans) return lasso_fused<T, 1, true, MODE>;
     switch (cpt) {
-        case 1: return lasso_fused<T, 1, false, FULL>;
-        case 2: return lasso_fused<T, 2, false, FULL>;
-        case 4: return lasso_fused<T, 4, false, FULL>;
-        case 8: return lasso_fused<T, 8, false, FULL>;
+        case 1: return lasso_fused<T, 1, false, MODE>;
+        case 2: return lasso_fused<T, 2, false, MODE>;
+        case 4: return lasso_fused<T, 4, false, MODE>;
+        case 8: return lasso_fused<T, 8, false, MODE>;
         default: return nullptr;
     }
 }
 
-// full = multi-GPU, tracing or diagnostic switches in use (see the FULL template parameter)
-static fused_fn ctx_kernel(const b200l_ctx *c, bool full) {
+// mode: 0 plain single GPU, 1 multi-GPU, 2 tracing or diagnostic switches in use (see MODE)
+static fused_fn ctx_kernel(const b200l_ctx *c, int mode) {
     const bool trans = c->layout == B200L_TRANSPOSED;
-    if (full)
-        return c->dtype == B200L_F32 ? pick_kernel<float, true>(c->cpt, trans) : pick_kernel<double, true>(c->cpt, trans);
-    return c->dtype == B200L_F32 ? pick_kernel<float, false>(c->cpt, trans) : pick_kernel<double, false>(c->cpt, trans);
+    const bool f32 = c->dtype == B200L_F32;
+    if (mode == 2) return f32 ? pick_kernel<float, 2>(c->cpt, trans) : pick_kernel<double, 2>(c->cpt, trans);
+    if (mode == 1) return f32 ? pick_kernel<float, 1>(c->cpt, trans) : pick_kernel<double, 1>(c->cpt, trans);
+    return f32 ? pick_kernel<float, 0>(c->cpt, trans) : pick_kernel<double, 0>(c->cpt, trans);
 }
 
 // tensor map of the pre-transposed matrix: 2-D (ldT residual entries, nblocks*w columns)
@@ -2623,8 +2668,8 @@ static int plan_geometry(b200l_ctx *c) {
         CK(cudaMemsetAsync(c->gLL, 0, need, c->stream));
     }
 
-    for (int full = 0; full < 2; ++full) {
-        fused_fn fn = ctx_kernel(c, full != 0);
+    for (int full = 0; full < 3; ++full) {
+        fused_fn fn = ctx_kernel(c, full);
         if (!fn) return fail("internal: no kernel for cpt=%d", cpt);
         CK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_bytes));
         int occ = 0;
@@ -2719,6 +2764,7 @@ static int launch_fused(b200l_ctx *c, const int32_t *order_host, int64_t nsteps,
     p.tile_sends = c->geo.tile_sends;
     p.xmode = c->geo.tile_sends ? 0 : 1;
     for (int r = 0; r < B200L_MAX_WORLD; ++r) p.peer[r] = c->peer[r];
+    p.mc = c->world > 1 ? c->mc : nullptr;
     p.dbg = c->dbg;
 
     if (c->world > 1)
@@ -2727,7 +2773,8 @@ static int launch_fused(b200l_ctx *c, const int32_t *order_host, int64_t nsteps,
                 return fail("multi-GPU run: the inbox of rank %d is not mapped (b200l_comm_connect has not "
                             "completed on this context)", r);
     if (c->layout == B200L_TRANSPOSED && !c->tmap_valid && make_tensor_map(c)) return 1;
-    fused_fn fn = ctx_kernel(c, c->world > 1 || trace_dev != nullptr || ttrace_dev != nullptr || (c->dbg & 7) != 0);
+    const bool diag = trace_dev != nullptr || ttrace_dev != nullptr || (c->dbg & 7) != 0;
+    fused_fn fn = ctx_kernel(c, diag ? 2 : ((c->world > 1 || (c->dbg & 4096)) ? 1 : 0));   // (dbg 4096: mode 1 on one GPU, to time the variant)
     void *args[] = {(void *)&p, (void *)&c->tmap};
     if (timed) CK(cudaEventRecord(c->ev0, c->stream));
     CK(cudaLaunchCooperativeKernel((const void *)fn, dim3(c->grid), dim3(NTHREADS), args,

@@ -76,13 +76,70 @@ def gather_x(x_local, BLOCK, group=None):
     return unshard_x([p.cpu().numpy() for p in parts], BLOCK)
 
 
-def connect(gpu_cal, group=None):
-    """export this rank's inbox, all-gather the IPC handles, map the peers (collective)."""
-    import torch
+def connect(gpu_cal, group=None, transport=None, multicast=None):
+    """Map the ranks' inboxes into each other (collective).
+
+    ``transport``: ``"symm"`` allocates the inbox as torch symmetric memory
+    (``torch.distributed._symmetric_memory``: peer mappings plus, on NVSwitch systems, a multicast
+    (NVLS) mapping, so the kernel sends a row with ONE ``multimem.st`` instead of ``world - 1`` peer
+    stores) and hands the plain addresses to ``b200l_comm_attach``; ``"ipc"`` uses the library's own
+    CUDA IPC export (``b200l_comm_export`` / ``_connect``).  Default (or ``B200L_COMM``): ``"auto"`` =
+    symmetric memory when it is available, else IPC.  ``multicast=False`` (or ``B200L_MULTICAST=0``)
+    keeps the unicast peer stores on a symmetric-memory inbox."""
+    import os
     dist = _dist()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     if world == 1:
-        return
+        return "single"
+    transport = transport or os.environ.get("B200L_COMM", "auto")
+    if multicast is None:
+        multicast = os.environ.get("B200L_MULTICAST", "1") != "0"
+    used = None
+    if transport in ("auto", "symm") and dist.get_backend(group) == "nccl":
+        try:
+            used = _connect_symm(gpu_cal, dist, group, rank, world, multicast)
+        except Exception as e:                      # no symmetric memory on this system / build
+            if transport == "symm":
+                raise
+            import warnings
+            warnings.warn("symmetric memory unavailable (%r); using CUDA IPC inboxes" % (e,))
+    if used is None:
+        _connect_ipc(gpu_cal, dist, group, rank, world)
+        used = "ipc"
+    gpu_cal._world, gpu_cal._rank, gpu_cal._group = world, rank, group
+    gpu_cal._transport = used
+    dist.barrier(group=group)
+    return used
+
+
+def _connect_symm(gpu_cal, dist, group, rank, world, multicast):
+    import torch
+    import torch.distributed._symmetric_memory as symm
+    lib = gpu_cal._lib
+    nbytes = ctypes.c_int64()
+    _lib.check(lib.b200l_comm_inbox_bytes(gpu_cal.ctx, world, ctypes.byref(nbytes)))
+    grp = group if group is not None else dist.group.WORLD
+    try:
+        symm.enable_symm_mem_for_group(grp.group_name)
+    except Exception:
+        pass
+    with torch.cuda.device(gpu_cal.device):
+        buf = symm.empty(int(nbytes.value), dtype=torch.uint8, device=gpu_cal.device)
+        buf.zero_()
+        hdl = symm.rendezvous(buf, grp)
+        torch.cuda.synchronize(gpu_cal.device)
+    ptrs = [int(a) for a in hdl.buffer_ptrs]
+    mc = int(getattr(hdl, "multicast_ptr", 0) or 0) if multicast else 0
+    dist.barrier(group=group)                        # every rank's inbox is zero-filled before anyone sends
+    arr = (ctypes.c_void_p * world)(*ptrs)
+    _lib.check(lib.b200l_comm_attach(gpu_cal.ctx, rank, world, arr, ctypes.c_void_p(mc) if mc else None))
+    gpu_cal._symm = (buf, hdl)                       # the memory must outlive the connection
+    return "symm+multicast" if mc else "symm"
+
+
+def _connect_ipc(gpu_cal, dist, group, rank, world):
+    """export this rank's inbox, all-gather the IPC handles, map the peers"""
+    import torch
     lib = gpu_cal._lib
     hb = _lib.IPC_HANDLE_BYTES
     mine = (ctypes.c_ubyte * hb)()
@@ -95,7 +152,6 @@ def connect(gpu_cal, group=None):
     blob = b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts)
     buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
     _lib.check(lib.b200l_comm_connect(gpu_cal.ctx, ctypes.cast(buf, ctypes.c_void_p), hb))
-    dist.barrier(group=group)
 
 
 def disconnect(gpu_cal, group=None):
@@ -106,3 +162,23 @@ def disconnect(gpu_cal, group=None):
     _lib.check(gpu_cal._lib.b200l_comm_close_peers(gpu_cal.ctx))
     dist.barrier(group=group)                                        # every mapping of my inbox is closed
     _lib.check(gpu_cal._lib.b200l_comm_destroy(gpu_cal.ctx))
+    gpu_cal._world, gpu_cal._rank, gpu_cal._group = 1, 0, None
+    gpu_cal._symm = None
+
+
+def objective(gpu_cal, mu, group=None):
+    """0.5 |Ax - b|^2 + mu |x|_1 of the whole instance: the residual is replicated on the ranks,
+    the l1 term is summed over the column shards"""
+    import torch
+    rss, l1 = ctypes.c_double(), ctypes.c_double()
+    _lib.check(gpu_cal._lib.b200l_objective_terms(gpu_cal.ctx, ctypes.byref(rss), ctypes.byref(l1)))
+    total_l1 = l1.value
+    if getattr(gpu_cal, '_world', 1) > 1:
+        dist = _dist()
+        grp = group if group is not None else gpu_cal._group
+        t = torch.tensor([l1.value], dtype=torch.float64)
+        if dist.get_backend(grp) == "nccl":
+            t = t.to(gpu_cal.device)
+        dist.all_reduce(t, group=grp)
+        total_l1 = float(t.item())
+    return 0.5 * rss.value + float(mu) * total_l1

@@ -182,9 +182,33 @@ class GPU_Calculation:
     # -- diag(A^T A) per block, (Block, w, 1) float64 (gpu_calculation.py:246-261) -------
     @property
     def diag_ATA(self):
+        # computed on the device once per matrix (one pass over A) and kept there; every access
+        # returns a fresh host array like the reference's .get() (gpu_calculation.py:261)
+        self._use_own_diag()
         out = np.empty((self.Block, self.MAT_WIDTH, 1), np.float64)
         _lib.check(self._lib.b200l_diag_ata(self.ctx, _lib.dptr(out)))
+        self._diag_host = out.copy()
         return out
+
+    def _use_own_diag(self):
+        if getattr(self, '_diag_is_custom', False):
+            _lib.check(self._lib.b200l_set_diag(self.ctx, None))
+            self._diag_is_custom = False
+
+    def _use_custom_diag(self, d_ATA):
+        """the solver was constructed with a diagonal that is not this matrix's own (the d_ATA
+        argument of the reference's solver classes, lasso.py:26-30): upload it for the fused path"""
+        d = np.ascontiguousarray(np.asarray(d_ATA, dtype=np.float64).reshape(self.Block, self.MAT_WIDTH))
+        _lib.check(self._lib.b200l_set_diag(self.ctx, _lib.dptr(d)))
+        self._diag_is_custom = True
+
+    def is_own_diag(self, d_ATA):
+        """True when ``d_ATA`` equals diag(A^T A) of the matrix on the device"""
+        own = getattr(self, '_diag_host', None)
+        if own is None:
+            own = self.diag_ATA
+        d = np.asarray(d_ATA)
+        return d.size == own.size and np.array_equal(d.reshape(own.shape), own)
 
     # -- s13 <- A_m^T s11 in place (gpu_calculation.py:264-277) ---------------------------
     def mat_tMulVec_DiffSize(self, s13, index_m, s11):

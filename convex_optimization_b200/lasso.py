@@ -166,6 +166,9 @@ class ClassLasso(ClassLassoCPU):
         self.gpu_cal = gpu_cal
         self.descript = 'GPU ascend index'
         self.kernel_ms = 0.0
+        # the fused kernel takes diag(A^T A) from the device; a caller-supplied d_ATA that differs
+        # from it (the reference lets the caller pass any, lasso.py:26-30) is uploaded per run
+        self._custom_diag = d_ATA is not None and not gpu_cal.is_own_diag(d_ATA)
 
     # matrix.T @ vector (ref lasso.py:183-184)
     def _mtv(self, s13, m, s11):
@@ -192,6 +195,32 @@ class ClassLasso(ClassLassoCPU):
                 'time_record': ClassLassoCPU.time_record}
         return any(getattr(cls, k) is not v for k, v in base.items())
 
+    def _shared_order(self, order):
+        """several GPUs: every rank must run the same block order (a randomised index_get draws
+        it independently per process), so rank 0's order is broadcast"""
+        if getattr(self.gpu_cal, '_world', 1) <= 1:
+            return order
+        import torch
+        import torch.distributed as dist
+        t = torch.from_numpy(order.copy())
+        if dist.get_backend(self.gpu_cal._group) == "nccl":
+            t = t.to(self.gpu_cal.device)
+        dist.broadcast(t, src=dist.get_global_rank(self.gpu_cal._group, 0) if self.gpu_cal._group is not None else 0,
+                       group=self.gpu_cal._group)
+        return np.ascontiguousarray(t.cpu().numpy().astype(np.int32))
+
+    def _fused_supported(self):
+        """the fused kernel has shape limits the reference does not (a row of a block must fit a
+        32 KiB tile, N / #SM <= 252 for the pre-transposed layout); shapes beyond them run the
+        step-wise path on the library's mat-vec kernels instead, with a warning"""
+        try:
+            self.gpu_cal.run_config()
+            return True
+        except _lib.B200LassoError as e:
+            import warnings
+            warnings.warn("fused kernel not available for this shape (%s); running the step-wise device path" % e)
+            return False
+
     def _fused(self, ERR_BOUND, err_iter, time_iter, SILENCE):
         """Whole solve in one persistent kernel (b200l_run)."""
         lib = self.gpu_cal._lib
@@ -204,6 +233,11 @@ class ClassLasso(ClassLassoCPU):
         bounded = isinstance(ERR_BOUND, float)
         order = np.fromiter((self.index_get(t) for t in range(self.ITER_MAX)),
                             dtype=np.int32, count=self.ITER_MAX)
+        order = self._shared_order(order)
+        if self._custom_diag:
+            self.gpu_cal._use_custom_diag(self.d_ATA)
+        else:
+            self.gpu_cal._use_own_diag()
         b = np.ascontiguousarray(self.b, dtype=np.float64).reshape(-1)
         errs = np.zeros(self.ITER_MAX) if self.ERR_RCD else None
         times = np.zeros(self.ITER_MAX) if self.TIME_RCD else None
@@ -248,7 +282,7 @@ class ClassLasso(ClassLassoCPU):
 
     def run(self, ERR_BOUND=None, err_iter=None, time_iter=None, SILENCE=False, DEBUG=False):
         self._run_flags(ERR_BOUND, err_iter, time_iter, DEBUG)
-        if self.FUSED and not DEBUG and not self._hooks_overridden():
+        if self.FUSED and not DEBUG and not self._hooks_overridden() and self._fused_supported():
             return self._fused(ERR_BOUND, err_iter, time_iter, SILENCE)
         return self._stepwise(ERR_BOUND, err_iter, time_iter, SILENCE, self._device_products)
 
@@ -279,6 +313,10 @@ class ClassLassoCB_v1(ClassLasso):
         self.idx_m = self.gpu_cal.MAT_HEIGHT
         self.idx_n = self.gpu_cal.MAT_WIDTH
 
+    # The reference overrides the two mat-vecs with cublasDgemv on device vectors (lasso.py:334-344).
+    # Here they are the same library mat-vecs as the parent's; the overrides exist so that
+    # _hooks_overridden() routes this class to the step-wise "host loop + device mat-vecs" path,
+    # which is what "Cublas CPU combined" is.
     def _mtv(self, result_s13, m, result_s11):
         self.gpu_cal.mat_tMulVec_DiffSize(result_s13, m, result_s11)
 
@@ -301,4 +339,6 @@ class ClassLassoCB_v2(ClassLasso):
 
     def run(self, ERR_BOUND=None, err_iter=None, time_iter=None, SILENCE=False, DEBUG=False):
         self._run_flags(ERR_BOUND, err_iter, time_iter, False)
+        if not self._fused_supported():
+            return self._stepwise(ERR_BOUND, err_iter, time_iter, SILENCE, self._device_products)
         return self._fused(ERR_BOUND, err_iter, time_iter, SILENCE)

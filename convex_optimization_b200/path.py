@@ -12,6 +12,7 @@ import os
 import numpy as np
 
 from . import _lib
+from . import distributed
 from . import settings
 
 
@@ -29,7 +30,8 @@ def lasso_path(gpu_cal, b, mus, BLOCK, ITER_MAX, ERR_BOUND=1e-4, collect_x=True)
     ``{mu, iters, stopped, objective, kernel_ms, x}`` (``x`` is ``(K,1)`` float64 or None).
 
     On several GPUs (``distributed.connect`` done) call it with the same arguments on every
-    rank; ``x`` is then the local slice."""
+    rank; ``x`` is then the local slice, ``objective`` the objective of the whole instance (the
+    l1 term is all-reduced over the ranks)."""
     lib, ctx = gpu_cal._lib, gpu_cal.ctx
     K = gpu_cal.MAT_WIDTH_ALL
     if BLOCK != gpu_cal.Block:
@@ -44,7 +46,7 @@ def lasso_path(gpu_cal, b, mus, BLOCK, ITER_MAX, ERR_BOUND=1e-4, collect_x=True)
         _lib.check(lib.b200l_run(ctx, None, int(ITER_MAX), float(mu),
                                  float(ERR_BOUND) if isinstance(ERR_BOUND, float) else -1.0, None, None,
                                  ctypes.byref(steps), ctypes.byref(stopped), ctypes.byref(kms)))
-        _lib.check(lib.b200l_objective(ctx, float(mu), ctypes.byref(obj)))
+        obj.value = distributed.objective(gpu_cal, mu)          # l1 term summed over the column shards
         x = None
         if collect_x:
             x = np.empty((K, 1), np.float64)

@@ -84,7 +84,8 @@ int b200l_gemv_t_dev(b200l_ctx *ctx, int32_t m, const double *r_dev, double *g_d
 int b200l_gemv_n_dev(b200l_ctx *ctx, int32_t m, const double *d_dev, double *q_dev);
 /* diag(A^T A) is computed once per bound matrix (one pass over A) and kept: b200l_diag_ata and
  * b200l_set_problem share it.  b200l_set_diag replaces it by the caller's values -- the d_ATA
- * argument of the solver classes (lasso.py:26-30), d_host[nblocks * w] doubles, block-major. */
+ * argument of the solver classes (lasso.py:26-30), d_host[nblocks * w] doubles, block-major;
+ * d_host = NULL goes back to the diagonal of the bound matrix. */
 int b200l_set_diag(b200l_ctx *ctx, const double *d_host);
 
 /* -- fused solver state -------------------------------------------------------------

@@ -142,6 +142,15 @@ def main():
             # the tile stamps are absolute, the phase stamps relative to the kernel start of the CTA
             fp = trf[:, BLOCK:, :] * scale
             off = ft[:, :, 16 + ntile - 1] - fp[:, :, 1]
+            if world > 1:
+                # my send of tile t -> my release of the peers' tile t; summed over two ranks it is the sum of
+                # the two one-way latencies "tile finished there -> row usable here" (the clocks cancel)
+                out["tiles_us"]["my rows of tile t sent -> all ranks' rows of tile t released here"] = \
+                    [round(float((ft[:, :, 80 + t] - ft[:, :, 64 + t]).mean()), 3) for t in range(ntile)]
+                out["tiles_us"]["pass2 tile t done -> my rows of tile t sent (sender warp)"] = \
+                    [round(float((ft[:, :, 64 + t] - ft[:, :, 48 + t]).mean()), 3) for t in range(ntile)]
+                out["tiles_us"]["all ranks' rows of tile t released -> next pass 1 reaches tile t"] = \
+                    [round(float((ft[:, 1:, t] - ft[:, :-1, 80 + t]).mean()), 3) for t in range(ntile)]
             out["tiles_us"]["pass2 tile 0 issued by the producer, after the end of gather g"] = \
                 round(float((ft[:, :, 80] - off - fp[:, :, 3]).mean()), 3)
             out["tiles_us"]["pass2 tile 0 landed, after the end of gather D"] = \
