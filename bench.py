@@ -18,7 +18,11 @@ between timed steps.
            GPU_Calculation(A, BLOCK), exactly as in the reference driver cpu_vs_gpu.py:131).
 `roofline`: algorithmic bytes of a sweep / kernel time vs the
            measured HBM copy peak of MEASURED_PEAKS.json.
-`cpu_baseline`: the oracle port of the reference's CPU path on a bounded sample.
+`cpu_baseline`: the reference's own ClassLassoCPU.run (oracle/_ref, an unmodified copy made by
+           oracle/make_ref.py) on a bounded sample; the NumPy port of the same loop beside it.
+N > 1 (torchrun): one C2-sized column shard per GPU (weak scaling); the line also carries an
+oracle-checked parity record of a small sharded solve and a C4-shard leg (50,000 x 125,000 fp32
+per GPU: 8 GPUs = BASELINE.json configs[3]).
 """
 import argparse
 import json
@@ -31,6 +35,13 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+
+# The CPU arm uses every host core it can: torchrun exports OMP_NUM_THREADS=1 to its workers, which
+# would pin NumPy's BLAS to one thread before it is even imported (round 1: the N>=2 reference
+# arm ran 7x slower than the N=1 one for this reason).
+if "reference" in sys.argv[1:]:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
 
 import numpy as np  # noqa: E402
 
@@ -201,77 +212,184 @@ def make_device_instance(torch, device, N, K, BLOCK, den, seed, torch_dtype, ld,
 
 
 # ------------------------------------------------------------------------------ CPU arm
-def cpu_sample(threads_note=True):
-    """the oracle port (NumPy/BLAS, all host threads) on a bounded C2-shaped sample:
-    10,000 x 10,000 fp64, 10 blocks of w=1000 (1/10 of C2's columns)."""
-    from oracle import lasso_oracle as orc
-    N, K, BLOCK = 10000, 10000, 10
-    rng = np.random.RandomState(2)
+C2_SAMPLE = dict(N=10000, K=3000, BLOCK=3)       # same block shape as C2 (10000 x 1000), 3 of its 100 blocks
+
+
+def blas_threads(n=None):
+    """set (when n is given) and return the BLAS thread count actually in use"""
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        if n:
+            threadpool_limits(limits=int(n))
+        info = [p.get("num_threads") for p in threadpool_info() if p.get("user_api") == "blas"]
+        return int(max(info)) if info else None
+    except Exception:
+        return None
+
+
+def cpu_sample(N, K, BLOCK, seed=2):
+    """C2-shaped sample on the host (reference recipe parameters.py:20-33, pinned seed)"""
+    rng = np.random.RandomState(seed)
     A = rng.standard_normal((N, K))
     A /= np.linalg.norm(A, axis=1, keepdims=True)
     xt = rng.standard_normal((K, 1)) * (rng.rand(K, 1) < 0.01)
     b = A @ xt + 1e-2 * rng.standard_normal((N, 1))
     mu = 0.1 * np.max(np.abs(A.T @ b))
-    return orc, A, b, mu, N, K, BLOCK
+    return A, b, float(mu)
 
 
-def run_cpu(orc, A, b, mu, BLOCK, sweeps):
-    """seconds spent in the iteration loop itself (the oracle times it like the reference's
-    run(), lasso.py:98,164); the one-off column norms and the final objective are outside"""
-    o = orc.lasso_oracle(A, b, mu, BLOCK, BLOCK * sweeps, None, faithful=False)
-    assert o["iters"] == BLOCK * sweeps
-    return o["elapsed"]
+def largest_divisor(n, limit):
+    return max(d for d in range(1, max(1, limit) + 1) if n % d == 0)
 
 
-def cpu_baseline_block(seconds=12.0):
-    """about `seconds` of CPU work: as many sweeps of the sample as fit (oracle time_limit)"""
-    orc, A, b, mu, N, K, BLOCK = cpu_sample()
-    run_cpu(orc, A, b, mu, BLOCK, 1)
+class RefCPU:
+    """the UNMODIFIED reference ClassLassoCPU (oracle/_ref/lasso.py:25-169; Pool(P) forked per
+    run(), lasso.py:101) on the C2-shaped sample.  One step = run() for BLOCK iterations = one
+    sweep of the sample; the time is what run() itself returns (lasso.py:98,164)."""
+
+    def __init__(self, P):
+        from oracle import make_ref
+        self.ref_lasso, _, self.ref_cpu = make_ref.import_reference()
+        N, K, BLOCK = C2_SAMPLE["N"], C2_SAMPLE["K"], C2_SAMPLE["BLOCK"]
+        self.A, self.b, self.mu = cpu_sample(N, K, BLOCK)
+        self.P, self.BLOCK, self.K = P, BLOCK, K
+        self.A_block_p = self.ref_cpu.A_bp_get(self.A, BLOCK, P)
+        self.d_ATA = self.ref_cpu.fun_diag_ATA(self.A_block_p)
+
+    def sweep_seconds(self):
+        solver = self.ref_lasso.ClassLassoCPU(self.A_block_p, self.d_ATA, self.A, self.b, self.mu,
+                                              self.BLOCK, self.P, self.BLOCK)
+        return float(solver.run(SILENCE=True))
+
+
+def port_sweeps_per_s(seconds):
+    """the NumPy port of the same loop (oracle/lasso_oracle.py), BLAS on all host threads, without
+    the reference's per-call Pool pickling: sample sweeps/s"""
+    from oracle import lasso_oracle as orc
+    N, K, BLOCK = C2_SAMPLE["N"], C2_SAMPLE["K"], C2_SAMPLE["BLOCK"]
+    A, b, mu = cpu_sample(N, K, BLOCK)
+    orc.lasso_oracle(A, b, mu, BLOCK, BLOCK, None, faithful=False)
     o = orc.lasso_oracle(A, b, mu, BLOCK, BLOCK * 100000, None, faithful=False, time_limit=seconds)
-    sweeps, dt = o["iters"] / float(BLOCK), o["elapsed"]
-    frac = K / C2["K"]
-    sample_sweeps_per_s = sweeps / dt
-    return {"value": sample_sweeps_per_s * frac, "unit": UNIT, "cores": os.cpu_count(),
-            "kind": "port",
-            "sample": "oracle port (NumPy fp64, BLAS threads) on 10000x10000, 10 blocks of w=1000 "
-                      "(1/10 of the C2 columns), %.1f sweeps in %.2f s = %.2f sample-sweeps/s; value is "
-                      "scaled by bytes (x%.2f) to the full 10000x100000 sweep" % (sweeps, dt, sample_sweeps_per_s, frac)}
+    return o["iters"] / float(BLOCK) / o["elapsed"]
+
+
+def ref_available():
+    try:
+        from oracle import make_ref
+        return make_ref.available()
+    except Exception:
+        return False
+
+
+def cpu_baseline_block(seconds=10.0):
+    """~20 s of CPU work on rank 0: the reference's own class on the sample (3 sweeps) and the port"""
+    cores = os.cpu_count() or 1
+    frac = C2_SAMPLE["K"] / float(C2["K"])
+    blas_threads(cores)
+    port = port_sweeps_per_s(min(seconds, 6.0)) * frac
+    shape = "%dx%d, %d blocks of w=%d (%d/100 of the C2 columns, same block shape)" % (
+        C2_SAMPLE["N"], C2_SAMPLE["K"], C2_SAMPLE["BLOCK"], C2_SAMPLE["K"] // C2_SAMPLE["BLOCK"], C2_SAMPLE["BLOCK"])
+    if not ref_available():
+        return {"value": port, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "oracle port (NumPy fp64, BLAS on %d threads) on %s; scaled by bytes (x%.3f) to C2; "
+                          "oracle/_ref is not populated on this box, so the reference class itself was not timed"
+                          % (cores, shape, frac)}
+    P = largest_divisor(C2_SAMPLE["K"] // C2_SAMPLE["BLOCK"], cores)
+    blas_threads(1)                                  # one BLAS thread per Pool worker
+    ref = RefCPU(P)
+    ref.sweep_seconds()
+    ts = [ref.sweep_seconds() for _ in range(2)]
+    value = frac / float(np.mean(ts))
+    return {"value": value, "unit": UNIT, "cores": P, "kind": "reference",
+            "sample": "unmodified ClassLassoCPU.run (oracle/_ref/lasso.py:70-169, Pool(P=%d), 1 BLAS thread per "
+                      "worker) on %s: %.2f s per sample sweep; scaled by bytes (x%.3f) to the C2 sweep"
+                      % (P, shape, float(np.mean(ts)), frac),
+            "port": {"value": port, "unit": UNIT, "cores": cores,
+                     "what": "the NumPy port of the same loop (oracle/lasso_oracle.py), BLAS on all host threads, "
+                             "no Pool pickling; same sample and scaling"}}
 
 
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    orc, A, b, mu, N, K, BLOCK = cpu_sample()
-    for _ in range(max(args.warmup, 1)):
-        run_cpu(orc, A, b, mu, BLOCK, 1)
-    dt = 0.0
-    for _ in range(args.steps):
-        dt += run_cpu(orc, A, b, mu, BLOCK, 1)
-    frac = K / C2["K"]
+    cores = os.cpu_count() or 1
+    frac = C2_SAMPLE["K"] / float(C2["K"])
+    shape = "%dx%d / %d-block sample of C2 (block shape 10000x1000 as in C2)" % (
+        C2_SAMPLE["N"], C2_SAMPLE["K"], C2_SAMPLE["BLOCK"])
+    extra = {}
+    if ref_available():
+        P = largest_divisor(C2_SAMPLE["K"] // C2_SAMPLE["BLOCK"], cores)
+        nblas = blas_threads(1)
+        ref = RefCPU(P)
+        for _ in range(max(args.warmup, 1)):
+            ref.sweep_seconds()
+        dt = sum(ref.sweep_seconds() for _ in range(args.steps))
+        kind, used = "reference", P
+        how = ("unmodified ClassLassoCPU.run (oracle/_ref/lasso.py:70-169) with Pool(P=%d) on %d host cores, %s BLAS "
+               "thread(s) per worker; each step = one sweep of a %s, scaled by bytes (x%.3f)" % (P, cores, nblas, shape, frac))
+        if args.gpus == 1 and not args.small:
+            # the driver's default worker count (cpu_vs_gpu.py:74) as a second point
+            P4 = largest_divisor(C2_SAMPLE["K"] // C2_SAMPLE["BLOCK"], min(4, cores))
+            r4 = RefCPU(P4)
+            r4.sweep_seconds()
+            extra["reference_P%d" % P4] = {"value": frac / r4.sweep_seconds(), "unit": UNIT, "cores": P4}
+            nb = blas_threads(cores)
+            extra["port"] = {"value": port_sweeps_per_s(6.0) * frac, "unit": UNIT, "cores": cores, "blas_threads": nb,
+                             "what": "NumPy port of the same loop, no Pool pickling"}
+            extra["c1_time_to_eps"] = c1_reference_time_to_eps(min(4, cores))
+    else:
+        from oracle import lasso_oracle as orc
+        nblas = blas_threads(cores)
+        A, b, mu = cpu_sample(C2_SAMPLE["N"], C2_SAMPLE["K"], C2_SAMPLE["BLOCK"])
+        BLOCK = C2_SAMPLE["BLOCK"]
+
+        def one():
+            return orc.lasso_oracle(A, b, mu, BLOCK, BLOCK, None, faithful=False)["elapsed"]
+        for _ in range(max(args.warmup, 1)):
+            one()
+        dt = sum(one() for _ in range(args.steps))
+        kind, used = "port", cores
+        how = ("oracle port (NumPy fp64, %s BLAS threads; oracle/_ref is not populated on this box); each step = one "
+               "sweep of a %s, scaled by bytes (x%.3f)" % (nblas, shape, frac))
     value = args.steps / dt * frac
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps / frac * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "dense lasso 10000x100000, 100 column blocks (C2); each step = one sweep "
-                               "of a 10000x10000 / 10-block sample, scaled by bytes"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                         "sample": "one sweep of a 10000x10000, 10-block fp64 sample per step; NumPy/BLAS "
-                                   "with all host threads; scaled x%.2f by bytes to C2" % frac},
+        "config": {"workload": "dense lasso 10000x100000, 100 column blocks (C2); " + how},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": how},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    line.update(extra)
     print(json.dumps(line))
     return 0
+
+
+def c1_reference_time_to_eps(P):
+    """BASELINE.json configs[0] on the reference itself: the default instance (cpu_vs_gpu.py:57-74) solved by
+    the unmodified ClassLassoCPU to ERR_BOUND = 1e-4"""
+    try:
+        from oracle import make_ref
+        ref_lasso, ref_par, ref_cpu = make_ref.import_reference()
+        ref_par.time = lambda: 1234
+        A, _, b, mu = ref_par.parameters(1024, 4096, 0.4, False, False, SILENCE=True)
+        Abp = ref_cpu.A_bp_get(A, 2, P)
+        solver = ref_lasso.ClassLassoCPU(Abp, ref_cpu.fun_diag_ATA(Abp), A, b, mu, 2, P, 1000)
+        err = np.zeros(1000)
+        secs = float(solver.run(1e-4, err_iter=err, SILENCE=True))
+        return {"workload": "default instance 1024x4096, BLOCK=2, P=%d, fp64, ERR_BOUND=1e-4" % P, "seconds": secs,
+                "iterations": int(np.count_nonzero(err))}
+    except Exception as e:                                  # pragma: no cover
+        return {"skipped": repr(e)}
 
 
 def c1_time_to_eps(device_index):
     """BASELINE.json configs[0]: the reference's default instance (cpu_vs_gpu.py:57-74: N=1024, K=4096,
     BLOCK=2, den=0.4, fp64, ERR_BOUND=1e-4, seed 1234) solved through ClassLasso.run() from host
-    arrays; reported beside the 52.45 s the unmodified ClassLassoCPU took in the survey
-    (BASELINE.md section 2).  Never fatal for the bench line."""
+    arrays; the reference arm times the unmodified ClassLassoCPU on the same instance.  Never fatal."""
     try:
         from convex_optimization_b200 import lasso, parameters
         from convex_optimization_b200.gpu_calculation import GPU_Calculation
@@ -281,15 +399,18 @@ def c1_time_to_eps(device_index):
             LAYOUT = "row"
             DEVICE = device_index
         A, _, b, mu = parameters.parameters(1024, 4096, 0.4, False, False, SILENCE=True, seed=1234)
+        t0 = time.time()
         cal = Cal(A, 2)
-        solver = lasso.ClassLasso(cal, cal.diag_ATA, A, b, mu, 2, 1000)
-        solver.run(1e-4, SILENCE=True)                      # warm-up (module load, first launch)
+        d = cal.diag_ATA
+        solver = lasso.ClassLasso(cal, d, A, b, mu, 2, 1000)
+        solver.run(1e-4, SILENCE=True)                      # includes module load / first launch
+        first = time.time() - t0
         t0 = time.time()
         solver.run(1e-4, SILENCE=True)
         dt = time.time() - t0
         return {"workload": "default instance 1024x4096, BLOCK=2, fp64, ERR_BOUND=1e-4 (cpu_vs_gpu.py:57-74)",
-                "seconds": dt, "iterations": int(solver.iters), "nnz_x": int(np.count_nonzero(solver.x)),
-                "api": "ClassLasso.run() (host b in, x out)",
+                "seconds": dt, "seconds_first_call_incl_upload": first, "iterations": int(solver.iters),
+                "nnz_x": int(np.count_nonzero(solver.x)), "api": "ClassLasso.run() (host b in, x out)",
                 "reference_cpu_seconds_survey": 52.45, "reference_iterations_survey": 128}
     except Exception as e:                                  # pragma: no cover
         sys.stderr.write("c1_time_to_eps skipped: %r\n" % (e,))
@@ -297,28 +418,230 @@ def c1_time_to_eps(device_index):
 
 
 # ------------------------------------------------------------------------------ GPU arm
-def main_gpu(args):
-    import torch
-    import torch.distributed as dist
-    from convex_optimization_b200 import _lib, lasso
+CONFIGS = {
+    "c2": dict(N=10000, K=100000, BLOCK=100, den=0.01, seed=2, dtype="float"),
+    # BASELINE.json configs[2]: fp64 20,000 x 200,000 (32 GB)
+    "c3": dict(N=20000, K=200000, BLOCK=100, den=0.01, seed=3, dtype="double"),
+    # one GPU's share of configs[3] on 8 GPUs: 50,000 x 125,000 fp32 (25 GB)
+    "c4shard": dict(N=50000, K=125000, BLOCK=100, den=0.01, seed=4, dtype="float"),
+}
+
+
+class Ctx:
+    """what every leg needs: torch, ranks, device, barrier, timing helpers"""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device("cuda", self.local_rank)
+        self.peak, self.peak_src = measured_peak()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.device)
+
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return float(v)
+        t = self.torch.tensor([v], device=self.device, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def cal_class(cfg, layout, local_rank):
     from convex_optimization_b200.gpu_calculation import GPU_Calculation
+
+    class Cal(GPU_Calculation):
+        TYPE = cfg["dtype"]
+        LAYOUT = layout
+        DEVICE = local_rank
+    return Cal
+
+
+def build_instance(cx, cfg, layout, instance, connect=True):
+    """(cal, b, mu): the local column shard of the instance on this rank's GPU"""
     import ctypes
+    from convex_optimization_b200 import _lib
+    torch = cx.torch
+    Cal = cal_class(cfg, layout, cx.local_rank)
+    N, K, BLOCK = cfg["N"], cfg["K"], cfg["BLOCK"]
+    if instance == "philox":
+        # the library's generator: the same global matrix for every world size (DESIGN.md 5c)
+        from convex_optimization_b200 import parameters as pm
+        cal, _, b, mu = pm.parameters_device(N, K * cx.world, BLOCK, cfg["den"], cfg["seed"], gpu_cal_cls=Cal)
+    else:
+        tdt = torch.float32 if cfg["dtype"] == "float" else torch.float64
+        ld = Cal.padded_ld(N, K, BLOCK)
+        store, b, mu = make_device_instance(torch, cx.device, N, K, BLOCK, cfg["den"], cfg["seed"], tdt, ld, layout,
+                                            cx.dist if cx.world > 1 else None, cx.rank)
+        cal = Cal.from_device_blocks(store, N, K, BLOCK)
+    stream = torch.cuda.current_stream(cx.device)
+    _lib.check(cal._lib.b200l_ctx_set_stream(cal.ctx, ctypes.c_void_p(stream.cuda_stream)))
+    transport = "single"
+    if cx.world > 1 and connect:
+        from convex_optimization_b200 import distributed as dd
+        transport = dd.connect(cal)
+    return cal, b, float(mu), transport
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
 
-    cfg = dict(C2)
+def time_sweeps(cx, cal, b, mu, BLOCK, steps, warmup, single_launch=False, sampler=None):
+    """device-timed sweeps of the fused kernel with everything resident: (ms per sweep, max over ranks)"""
+    import ctypes
+    from convex_optimization_b200 import _lib
+    torch = cx.torch
+    lib, ctx = cal._lib, cal.ctx
+    bb = np.ascontiguousarray(b.reshape(-1))
+    _lib.check(lib.b200l_set_problem(ctx, _lib.dptr(bb)))
+
+    def sweeps(n):
+        if not single_launch:
+            for _ in range(n):
+                _lib.check(lib.b200l_run(ctx, None, BLOCK, float(mu), -1.0, None, None, None, None, None))
+        elif n > 0:
+            _lib.check(lib.b200l_run(ctx, None, BLOCK * n, float(mu), -1.0, None, None, None, None, None))
+    sweeps(warmup)
+    cx.barrier()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    ev0.record()
+    sweeps(steps)
+    ev1.record()
+    cx.barrier()
+    t1 = time.time()
+    ms = cx.max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.stop(t0, t1) if sampler is not None else None
+    return ms / steps, clocks
+
+
+def roofline_record(cx, cfg, layout, ms_per_sweep, sweeps_per_launch, traffic_key, l2_bytes):
+    N, K, BLOCK = cfg["N"], cfg["K"], cfg["BLOCK"]
+    s = 4 if cfg["dtype"] == "float" else 8
+    W = sweep_bytes(N, K, BLOCK, s)
+    achieved = W / (ms_per_sweep * 1e-3) / 1e9
+    traffic_sweep = ncu_traffic(*traffic_key) if traffic_key else None
+    block_mb = N * (K // BLOCK) * s / 1e6
+    resident = 2 * N * (K // BLOCK) * s <= l2_bytes * 3 // 4
+    rec = {"bound": "hbm", "achieved": achieved, "peak": cx.peak, "unit": "GB/s", "frac": achieved / cx.peak,
+           "traffic": None if traffic_sweep is None else traffic_sweep * sweeps_per_launch,
+           "kernel": "lasso_fused<%s,%s>" % ("float" if s == 4 else "double", "TRANS" if layout == "transposed" else "ROWMAJOR"),
+           "kernel_ms_per_launch": ms_per_sweep * sweeps_per_launch, "sweeps_per_launch": sweeps_per_launch,
+           "algorithmic_bytes_per_launch": W * sweeps_per_launch, "algorithmic_bytes_per_sweep": W,
+           "traffic_per_sweep": traffic_sweep, "peak_source": cx.peak_src,
+           "frac_of_nominal_8TBs": achieved / 8000.0,
+           "frac_dram": None if traffic_sweep is None else traffic_sweep / (ms_per_sweep * 1e-3) / 1e9 / cx.peak,
+           "note": ("algorithmic bytes count A twice per sweep (SURVEY 8d); a %.0f MB block and its successor fit in L2, so "
+                    "the second pass is served by L2 and DRAM moves about half of the algorithmic bytes: frac_dram is "
+                    "the DRAM bytes of the committed ncu capture / time / peak" % block_mb) if resident else
+                   ("algorithmic bytes count A twice per sweep (SURVEY 8d); a %.0f MB block does not stay in L2, both "
+                    "passes stream from HBM: DRAM traffic = algorithmic bytes" % block_mb)}
+    return rec
+
+
+def parity_record(cx):
+    """a small column-sharded solve on this world size against the oracle with P = world (the reference's
+    own P-way split, lasso.py:107-126): iterations, support, x; rc != 0 on mismatch"""
+    from oracle import lasso_oracle as orc
+    from convex_optimization_b200 import distributed as dd
+    from convex_optimization_b200 import lasso
+    world, rank = cx.world, cx.rank
+    out = []
+    for (N, K, BLOCK, den, TYPE, seed) in [(600, 512 * world, 4, 0.05, "double", 7), (1000, 1000 * world, 2, 0.02, "float", 5)]:
+        A, _, b, mu = orc.make_problem(N, K, den, seed=seed)
+        if TYPE == "float":
+            A = A.astype(np.float32).astype(np.float64)
+        ITER_MAX = 100 * BLOCK if TYPE == "double" else 12 * BLOCK
+        bound = 1e-4 if TYPE == "double" else None
+        o = orc.lasso_oracle(A, b, mu, BLOCK, ITER_MAX, bound, P=world, faithful=False)
+        Cal = cal_class(dict(dtype=TYPE), "row", cx.local_rank)
+        A_loc = dd.shard_columns(A, BLOCK, rank, world) if world > 1 else A
+        cal = Cal(A_loc, BLOCK)
+        if world > 1:
+            dd.connect(cal)
+        solver = lasso.ClassLasso(cal, cal.diag_ATA, A_loc, b, mu, BLOCK, ITER_MAX)
+        solver.run(bound, SILENCE=True)
+        x = dd.gather_x(solver.x, BLOCK) if world > 1 else solver.x
+        obj = dd.objective(cal, mu)
+        xo = o["x"]
+        rel = float(np.abs(x - xo).max() / np.abs(xo).max())
+        small = np.abs(xo) < 1e-5 * np.abs(xo).max()
+        mism = (x != 0) != (xo != 0)
+        obj_o = 0.5 * float(np.sum((A @ xo - b) ** 2)) + mu * float(np.abs(xo).sum())
+        tol = 1e-10 if TYPE == "double" else 1e-5
+        ok = (rel < tol and solver.iters == o["iters"] and abs(obj - obj_o) <= tol * abs(obj_o)
+              and (not mism.any() if TYPE == "double" else bool(np.all(small[mism]))))
+        out.append({"shape": "%dx%d b%d %s" % (N, K, BLOCK, TYPE), "world": world, "rel_x": rel, "rel_obj": abs(obj - obj_o) / abs(obj_o),
+                    "support_equal": bool(not mism.any()), "support_mismatches_all_below_1e-5_of_max": bool(np.all(small[mism])),
+                    "iters": int(solver.iters), "iters_oracle": int(o["iters"]), "ok": bool(ok)})
+        if world > 1:
+            dd.disconnect(cal)
+        del solver, cal
+    return out
+
+
+def leg(cx, name, cfg, layout, instance, steps, warmup, traffic_key, l2_bytes, standalone_first=False):
+    """one timed configuration as a sub-record"""
+    torch = cx.torch
+    cal, b, mu, transport = build_instance(cx, cfg, layout, instance, connect=False)
+    rec = {"workload": "dense %s lasso %dx%d, %d column blocks, %s layout%s" % (
+        "fp32" if cfg["dtype"] == "float" else "fp64", cfg["N"], cfg["K"] * cx.world, cfg["BLOCK"], layout,
+        (", column-sharded over %d GPUs (%dx%d per GPU)" % (cx.world, cfg["N"], cfg["K"])) if cx.world > 1 else ""),
+        "instance": instance}
+    ms1 = None
+    if cx.world > 1 and standalone_first:
+        # this rank's shard as a 1-GPU problem (the same matrix), then the sharded solve: efficiency
+        ms1, _ = time_sweeps(Ctx1(cx), cal, b, mu, cfg["BLOCK"], steps, warmup)
+        rec["ms_per_sweep_1gpu_shard"] = cx.max_over_ranks(ms1)
+    if cx.world > 1:
+        from convex_optimization_b200 import distributed as dd
+        rec["transport"] = dd.connect(cal)
+    ms, _ = time_sweeps(cx, cal, b, mu, cfg["BLOCK"], steps, warmup)
+    rec.update({"ms_per_sweep": ms, "value": cx.world * 1e3 / ms, "unit": UNIT, "instance_sweeps_per_s": 1e3 / ms,
+                "launch": cal.run_config()})
+    roof = roofline_record(cx, cfg, layout, ms, 1, traffic_key, l2_bytes)
+    rec["roofline"] = {k: roof[k] for k in ("achieved", "peak", "frac", "frac_dram", "traffic_per_sweep", "algorithmic_bytes_per_sweep", "note")}
+    if ms1 is not None:
+        rec["efficiency_vs_1gpu_shard"] = rec["ms_per_sweep_1gpu_shard"] / ms
+        rec["frac_of_aggregate_roofline"] = roof["frac"]
+    if cx.world > 1:
+        from convex_optimization_b200 import distributed as dd
+        dd.disconnect(cal)
+    del cal
+    torch.cuda.empty_cache()
+    return rec
+
+
+class Ctx1:
+    """a view of Ctx that behaves like a single-GPU run (no cross-rank barrier inside the timing)"""
+
+    def __init__(self, cx):
+        self.torch, self.device, self.world = cx.torch, cx.device, 1
+
+    def barrier(self):
+        self.torch.cuda.synchronize(self.device)
+
+    def max_over_ranks(self, v):
+        return float(v)
+
+
+def main_gpu(args):
+    import ctypes
+    from convex_optimization_b200 import _lib, lasso
+    cx = Ctx()
+    torch, world, rank, local_rank, device = cx.torch, cx.world, cx.rank, cx.local_rank, cx.device
+    l2_bytes = torch.cuda.get_device_properties(device).L2_cache_size
+
+    cfg = dict(CONFIGS[args.config])
     if args.small:
         cfg.update(N=2000, K=20000, BLOCK=20)
-    if args.config == "c3":       # BASELINE.json configs[2]: fp64 20,000 x 200,000 (32 GB), not the bench line
-        cfg.update(N=20000, K=200000, BLOCK=100, dtype="double", seed=3)
-    elif args.config == "c4shard":  # one GPU's share of configs[3] on 8 GPUs: 50,000 x 125,000 fp32 (25 GB)
-        cfg.update(N=50000, K=125000, BLOCK=100, dtype="float", seed=4)
     if args.shape:              # diagnostics only: N,K,BLOCK[,dtype]
         f = args.shape.split(",")
         cfg.update(N=int(f[0]), K=int(f[1]), BLOCK=int(f[2]))
@@ -327,134 +650,89 @@ def main_gpu(args):
     N, K, BLOCK = cfg["N"], cfg["K"], cfg["BLOCK"]
     s = 4 if cfg["dtype"] == "float" else 8
     layout = args.layout
+    quick = args.small or bool(args.shape) or args.quick
 
-    class Cal(GPU_Calculation):
-        TYPE = cfg["dtype"]
-        LAYOUT = layout
-        DEVICE = local_rank
-    ld = Cal.padded_ld(N, K, BLOCK)
-    tdt = torch.float32 if cfg["dtype"] == "float" else torch.float64
-    # N GPUs: the instance grows with N (weak scaling): K = 100000*N columns, 100 blocks of width
-    # 1000*N, column slice `rank` of every block per GPU, i.e. one C2-sized shard per GPU
-    if args.instance == "philox":
-        # the library's generator: the same global matrix for every world size
-        from convex_optimization_b200 import parameters as pm
-        cal, _, b, mu = pm.parameters_device(N, K * world, BLOCK, cfg["den"], cfg["seed"], gpu_cal_cls=Cal)
-    else:
-        store, b, mu = make_device_instance(torch, device, N, K, BLOCK, cfg["den"], cfg["seed"], tdt, ld, layout,
-                                            dist if world > 1 else None, rank)
-        cal = Cal.from_device_blocks(store, N, K, BLOCK)
-    if world > 1:
-        from convex_optimization_b200 import distributed as dd
-        dd.connect(cal)
+    # ---- parity first: a wrong kernel must not print a number -------------------------------
+    parity = None
+    if not args.no_parity:
+        parity = parity_record(cx)
+        if not all(p["ok"] for p in parity):
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "error": "parity check against the oracle failed", "parity": parity}))
+            return 3
+
+    # ---- headline: C2 (one C2-sized shard per GPU), resident, device-timed --------------------
+    cal, b, mu, transport = build_instance(cx, cfg, layout, args.instance)
     if args.slot_bytes or args.inflight:
         cal.set_tuning(args.slot_bytes, args.inflight)
     lib, ctx = cal._lib, cal.ctx
     if args.dbg:
         _lib.check(lib.b200l_debug_flags(ctx, args.dbg))
-    # the library launches on the stream the CUDA events below are recorded on
-    stream = torch.cuda.current_stream(device)
-    _lib.check(lib.b200l_ctx_set_stream(ctx, ctypes.c_void_p(stream.cuda_stream)))
+    t0 = time.time()
     d_ATA = cal.diag_ATA
+    torch.cuda.synchronize(device)
+    setup_ms = (time.time() - t0) * 1e3
     geo = cal.run_config()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(device)
-
-    # ---- value: K sweeps, resident, device-timed ------------------------------------
-    bb = np.ascontiguousarray(b.reshape(-1))
-    _lib.check(lib.b200l_set_problem(ctx, _lib.dptr(bb)))
-
-    # One launch of the persistent kernel per timed sweep (the unit the roofline and the committed
-    # ncu launch list refer to); --single-launch runs the K sweeps in one launch, like a solve.
-    def sweeps(n):
-        if not args.single_launch:
-            for _ in range(n):
-                _lib.check(lib.b200l_run(ctx, None, BLOCK, float(mu), -1.0, None, None, None, None, None))
-        elif n > 0:
-            _lib.check(lib.b200l_run(ctx, None, BLOCK * n, float(mu), -1.0, None, None, None, None, None))
-
     # (the sampler starts before the warm-up: its start-up must not delay rank 0 behind the others)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    sweeps(args.warmup)
-    barrier()
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.time()
-    ev0.record()
-    sweeps(args.steps)
-    ev1.record()
-    barrier()
-    t_wall1 = time.time()
-    ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms_per_step = ms / args.steps
+    ms_per_step, clocks = time_sweeps(cx, cal, b, mu, BLOCK, args.steps, args.warmup, args.single_launch,
+                                      sampler if rank == 0 else None)
     value = world * 1e3 / ms_per_step
-
-    # the timed region is K launches of the one kernel on this stream, so its average launch
-    # duration is ms_per_step; the same launch timed alone (events inside the library, a host
-    # synchronisation after each) is reported beside it
+    sweeps_per_launch = args.steps if args.single_launch else 1
+    n_launches = args.steps // sweeps_per_launch
     kms = ctypes.c_double()
     ktimes = []
     for _ in range(min(args.steps, 10)):
-        _lib.check(lib.b200l_run(ctx, None, BLOCK, float(mu), -1.0, None, None, None, None,
-                                 ctypes.byref(kms)))
+        _lib.check(lib.b200l_run(ctx, None, BLOCK, float(mu), -1.0, None, None, None, None, ctypes.byref(kms)))
         ktimes.append(kms.value)
-    sweeps_per_launch = args.steps if args.single_launch else 1
-    n_launches = args.steps // sweeps_per_launch
-    kernel_ms = ms / n_launches                  # average duration of the launches of the timed region
-    kernel_ms_alone = float(np.mean(ktimes))
-    obj = ctypes.c_double()
-    _lib.check(lib.b200l_objective(ctx, float(mu), ctypes.byref(obj)))
-    obj_bench = obj.value
+    from convex_optimization_b200 import distributed as dd
+    obj_bench = dd.objective(cal, mu)
 
-    # ---- e2e: through ClassLasso.run(), host b in, host x out -------------------------
+    # ---- e2e: through ClassLasso.run(), host b in, host x out -------------------------------
     e2e_sweeps = args.e2e_sweeps
+
     class HostShape:            # the solver only needs A.shape on the fused path (lasso.py:32)
         shape = (N, K)
     solver = lasso.ClassLasso(cal, d_ATA, HostShape, b, mu, BLOCK, BLOCK * e2e_sweeps)
     for _ in range(2):
         solver.run(SILENCE=True)
-    barrier()
+    cx.barrier()
     t0 = time.time()
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(e2e_steps):
         solver.run(SILENCE=True)
-    barrier()
-    e2e_dt = time.time() - t0
-    if world > 1:
-        t = torch.tensor([e2e_dt], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_dt = float(t.item())
+    cx.barrier()
+    e2e_dt = cx.max_over_ranks(time.time() - t0)
     e2e_value = world * e2e_steps * e2e_sweeps / e2e_dt
     nnz = int(np.count_nonzero(solver.x))
 
     # ---- time-to-eps: cold start (x = 0) to the reference's stop rule (lasso.py:141-150) ----
     tte = None
     if args.eps > 0:
-        _lib.check(lib.b200l_reset(ctx))
+        bb = np.ascontiguousarray(b.reshape(-1))
+        x_host = np.empty((K, 1))
+        cx.barrier()
+        t0 = time.time()
+        _lib.check(lib.b200l_set_problem(ctx, _lib.dptr(bb)))
         steps_done, stopped = ctypes.c_int64(), ctypes.c_int32()
         _lib.check(lib.b200l_run(ctx, None, BLOCK * args.eps_max_sweeps, float(mu), float(args.eps), None, None,
                                  ctypes.byref(steps_done), ctypes.byref(stopped), ctypes.byref(kms)))
-        _lib.check(lib.b200l_objective(ctx, float(mu), ctypes.byref(obj)))
+        _lib.check(lib.b200l_get_x(ctx, _lib.dptr(x_host)))
+        wall_ms = (time.time() - t0) * 1e3
         tte = {"eps": args.eps, "ms": kms.value, "sweeps": steps_done.value / BLOCK,
-               "reached": bool(stopped.value), "objective": obj.value,
-               "note": "device time of one launch from x = 0 until every block of a sweep has error_crit < eps"}
+               "reached": bool(stopped.value), "objective": dd.objective(cal, mu),
+               "e2e_ms": wall_ms + setup_ms, "setup_ms": setup_ms,
+               "note": "ms: device time of the one launch from x = 0 until every block of a sweep has error_crit < eps; "
+                       "e2e_ms: diag(A^T A) (one pass over A, setup_ms) + b to the device + that launch + x to the host"}
 
+    line = None
     if rank == 0:
-        W = sweep_bytes(N, K, BLOCK, s)
-        peak, peak_src = measured_peak()
-        achieved = W * sweeps_per_launch / (kernel_ms * 1e-3) / 1e9
-        traffic_sweep = None if args.small else ncu_traffic(args.config, layout)
-        traffic = None if traffic_sweep is None else traffic_sweep * sweeps_per_launch
+        roof = roofline_record(cx, cfg, layout, ms_per_step, sweeps_per_launch,
+                               None if quick else (args.config, layout), l2_bytes)
+        roof["ms_per_single_sweep_launch_alone"] = float(np.mean(ktimes))
+        roof["dram_single_pass_GBs"] = (roof["algorithmic_bytes_per_sweep"] - N * K * s) / (ms_per_step * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -466,23 +744,11 @@ def main_gpu(args):
                                    % ("fp32" if s == 4 else "fp64", N, K * world, BLOCK, layout, n_launches,
                                       N * K * s / 1e9,
                                       ("; column-sharded over %d GPUs (slice g of every block on GPU g, partial "
-                                       "A_m D summed in-kernel over NVLink peer memory); value counts C2-sized "
-                                       "shard sweeps: %d per sweep of the %dx%d instance"
-                                       % (world, world, N, K * world)) if world > 1 else ""),
+                                       "A_m D summed in-kernel over NVLink peer memory, transport %s); value counts "
+                                       "C2-sized shard sweeps: %d per sweep of the %dx%d instance"
+                                       % (world, transport, world, N, K * world)) if world > 1 else ""),
                        "launch": geo, "objective_after_bench": obj_bench},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "lasso_fused<%s,1,%s>" % ("float" if s == 4 else "double",
-                                                             "TRANS" if layout == "transposed" else "ROWMAJOR"),
-                         "kernel_ms_per_launch": kernel_ms, "sweeps_per_launch": sweeps_per_launch,
-                         "ms_per_single_sweep_launch_alone": kernel_ms_alone,
-                         "algorithmic_bytes_per_launch": W * sweeps_per_launch,
-                         "algorithmic_bytes_per_sweep": W, "traffic_per_sweep": traffic_sweep,
-                         "peak_source": peak_src,
-                         "frac_of_nominal_8TBs": achieved / 8000.0,
-                         "dram_single_pass_GBs": (W - N * K * s) * sweeps_per_launch / (kernel_ms * 1e-3) / 1e9,
-                         "note": "algorithmic bytes count A twice per sweep (SURVEY 8d); the second pass of a "
-                                 "40 MB block is served by L2, so DRAM traffic is about half of it (see traffic)"},
+            "roofline": roof,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(N * 8 + 4 * BLOCK * e2e_sweeps),
                     "d2h_bytes_per_step": int(K * 8 + 24),
@@ -491,9 +757,34 @@ def main_gpu(args):
             "gpu_launches": n_launches,
             "clocks": clocks,
         }
+        if world > 1:
+            line["value_counts"] = "C2-sized shard sweeps summed over the GPUs (weak scaling)"
+            line["instance_sweeps_per_s"] = 1e3 / ms_per_step
+        if parity is not None:
+            line["parity"] = parity
         if tte:
             line["time_to_eps"] = tte
-        if world == 1 and not args.small and args.eps > 0:
+    if world > 1:
+        dd.disconnect(cal)
+    del solver, cal
+    torch.cuda.empty_cache()
+
+    # ---- the other configurations of BASELINE.json as sub-records ---------------------------------
+    others = {}
+    if not quick and args.config == "c2":
+        nsw = max(3, min(args.steps, 5))
+        if world == 1:
+            others["c2_transposed"] = leg(cx, "c2_transposed", CONFIGS["c2"], "transposed", "torch", args.steps, 3,
+                                          ("c2", "transposed"), l2_bytes)
+            others["c3_fp64"] = leg(cx, "c3", CONFIGS["c3"], "row", "torch", nsw, 2, ("c3", "row"), l2_bytes)
+        # C4: one 50,000 x 125,000 shard per GPU (8 GPUs = the 50k x 1M instance), Philox instance: the same
+        # global matrix for every world size
+        others["c4_shard_per_gpu"] = leg(cx, "c4shard", CONFIGS["c4shard"], "row", "philox", nsw, 2,
+                                         ("c4shard", "row"), l2_bytes, standalone_first=True)
+    if rank == 0:
+        if others:
+            line["configs"] = others
+        if world == 1 and not quick and args.eps > 0:
             c1 = c1_time_to_eps(local_rank)
             if c1:
                 line["c1_time_to_eps"] = c1
@@ -501,8 +792,7 @@ def main_gpu(args):
             line["cpu_baseline"] = cpu_baseline_block()
         print(json.dumps(line))
     if world > 1:
-        dd.disconnect(cal)
-        dist.destroy_process_group()
+        cx.dist.destroy_process_group()
     return 0
 
 
@@ -514,7 +804,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layout", default="row", choices=["row", "transposed"])
     ap.add_argument("--small", action="store_true", help="2000x20000 debug size (not a bench value)")
+    ap.add_argument("--quick", action="store_true", help="headline leg only (no sub-records of the other configurations)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle-checked solve in front of the timing")
     ap.add_argument("--e2e-sweeps", type=int, default=5)
     ap.add_argument("--instance", default="torch", choices=["torch", "philox"],
                     help="how the synthetic instance is generated on the device: torch RNG per rank (default) or "
@@ -528,7 +820,7 @@ def main():
     ap.add_argument("--dbg", type=int, default=0, help="diagnostic flags of b200l_debug_flags (not for bench values)")
     ap.add_argument("--shape", default="", help="diagnostics: N,K,BLOCK[,float|double] instead of a named config")
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4shard"],
-                    help="c2 is the bench workload; the others are reported in DESIGN.md only")
+                    help="c2 is the bench workload; the others appear as sub-records of the default run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

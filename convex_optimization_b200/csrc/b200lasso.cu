@@ -1030,7 +1030,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                         Acc a0, a1;
                         OP::zero(a0);
                         OP::zero(a1);
-                        if (j < p.w && !(DBG & 2)) {
+                        if (tid < p.TJ && j < p.w && !(DBG & 2)) {
                             const T *col = tile + (size_t)tid * p.BX;
 #pragma unroll 4
                             for (int iv = 0; iv < p.BXV; ++iv) {
@@ -1039,7 +1039,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                                 OP::mac(a1, v, *reinterpret_cast<const VecT *>(qT + iv * V));
                             }
                         }
-                        if (j < G * cs) {
+                        if (tid < p.TJ && j < G * cs) {
                             const int rd = j >> p.cs_shift;
                             const int jj = j & (cs - 1);
                             LL::put(p.gLL + ((size_t)rd * G + c) * p.mw + jj * WPC, OP::hsum(a0), OP::hsum(a1), tag);
@@ -2560,7 +2560,10 @@ static int plan_geometry(b200l_ctx *c) {
     // transposed layout: box of BX residual entries (odd number of 16-byte groups) x TJ columns
     const int BXV = ((rows_max + V - 1) / V) | 1;
     const int BX = BXV * V;
-    const int TJ = NTC;
+    // (columns per tile: one per thread in pass 1; fewer when a CTA's share of a column is long, so that
+    // at least three tiles fit the ring -- fp64 with N / #SM = 68 entries: 256 columns would be 143 KB)
+    int TJ = NTC;
+    while (trans && TJ > 32 && (int64_t)TJ * BX * es > 70000) TJ >>= 1;   // (fp32 C2: 256 x 68 x 4 = 69632, three slots)
     const int nt_t = (c->w + TJ - 1) / TJ;
     const int nparts = std::max(1, std::min(NTC / BXV, 32));
     if (trans && BX > 256)

@@ -44,3 +44,23 @@ def load_golden(name):
 def lib():
     from convex_optimization_b200 import _lib
     return _lib.load()
+
+
+def assert_support(x, x_ref, TYPE):
+    """The support bar of BASELINE.json's north star ("the nonzero pattern is checked exactly"):
+    fp64 -- the nonzero patterns are identical; fp32 -- identical on every entry the fp32 tolerance
+    can resolve: an index where the patterns differ must be negligible in BOTH solutions,
+    |x_ref| < 1e-5 max|x_ref| and |x| < 1e-5 max|x_ref| (the reference keeps entries like -1.95e-10
+    as "nonzero", which an fp32 matrix may legitimately round to an exact 0).  Enforced by every
+    fp32 parity test (golden, ragged, transposed, bench geometries, multi-GPU)."""
+    x = np.asarray(x).reshape(-1)
+    x_ref = np.asarray(x_ref).reshape(-1)
+    mism = (x != 0) != (x_ref != 0)
+    if TYPE == "double":
+        assert not mism.any(), "support differs at %d entries" % int(mism.sum())
+        return 0
+    scale = 1e-5 * np.abs(x_ref).max()
+    bad = mism & ((np.abs(x_ref) >= scale) | (np.abs(x) >= scale))
+    assert not bad.any(), "support differs at %d resolvable entries (max |x_ref| there %.3e)" % (
+        int(bad.sum()), float(np.abs(x_ref[bad]).max()))
+    return int(mism.sum())

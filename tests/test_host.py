@@ -106,31 +106,26 @@ def test_compute_fails_loudly_without_gpu():
 
 
 def test_bench_reference_arm_prints_the_contract_line(monkeypatch, capsys):
-    """bench.py --impl reference: one JSON line with the keys of the bench contract (small sample here)"""
+    """bench.py --impl reference: one JSON line with the keys of the bench contract (small sample here),
+    timed on the unmodified reference class when oracle/_ref is populated, else on the port"""
     import argparse
     import json
     import bench
-    from oracle import lasso_oracle as orc
 
-    def small_sample(threads_note=True):
-        rng = np.random.RandomState(2)
-        N, K, BLOCK = 200, 400, 4
-        A = rng.standard_normal((N, K))
-        A /= np.linalg.norm(A, axis=1, keepdims=True)
-        xt = rng.standard_normal((K, 1)) * (rng.rand(K, 1) < 0.05)
-        b = A @ xt + 1e-2 * rng.standard_normal((N, 1))
-        return orc, A, b, 0.1 * np.max(np.abs(A.T @ b)), N, K, BLOCK
-
-    monkeypatch.setattr(bench, "cpu_sample", small_sample)
+    monkeypatch.setattr(bench, "C2_SAMPLE", dict(N=200, K=400, BLOCK=4))
+    monkeypatch.setattr(bench, "c1_reference_time_to_eps", lambda P: {"skipped": "test"})
+    monkeypatch.setattr(bench, "port_sweeps_per_s", lambda seconds: 1.0)
     monkeypatch.delenv("RANK", raising=False)
-    args = argparse.Namespace(gpus=1, steps=2, warmup=1)
+    args = argparse.Namespace(gpus=1, steps=2, warmup=1, small=False)
     assert bench.main_reference(args) == 0
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line
     assert line["impl"] == "reference" and line["metric"] == bench.METRIC and line["value"] > 0
-    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] == ("reference" if bench.ref_available() else "port")
+    assert line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
     # other ranks of a torchrun launch exit without work
     monkeypatch.setenv("RANK", "1")
     assert bench.main_reference(args) == 0
