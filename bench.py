@@ -677,10 +677,14 @@ def main_gpu(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_per_step, clocks = time_sweeps(cx, cal, b, mu, BLOCK, args.steps, args.warmup, args.single_launch,
+    # several GPUs: the K timed sweeps run in ONE launch per rank, the way a solve runs (every launch
+    # boundary makes the ranks meet again after the host-side launch skew of 8 processes); one GPU:
+    # one launch per sweep, the unit the roofline record and the committed ncu launch list refer to
+    single_launch = args.single_launch or world > 1
+    ms_per_step, clocks = time_sweeps(cx, cal, b, mu, BLOCK, args.steps, args.warmup, single_launch,
                                       sampler if rank == 0 else None)
     value = world * 1e3 / ms_per_step
-    sweeps_per_launch = args.steps if args.single_launch else 1
+    sweeps_per_launch = args.steps if single_launch else 1
     n_launches = args.steps // sweeps_per_launch
     kms = ctypes.c_double()
     ktimes = []

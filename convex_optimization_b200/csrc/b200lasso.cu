@@ -729,6 +729,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                 double trq = 0.0, tqq = 0.0;
                 int own_rows = 0;                            // my own rows below this index are final
                 int rel_t = 0;                               // (trace) tiles whose rows have been released
+                int last_ready = -1;
                 unsigned spin = 0;
                 // nothing can arrive before the ranks are in pass 2 of this step: nap until mine
                 // begins (shared-memory flag, no L2 traffic)
@@ -830,6 +831,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                                 p.ttrace[((size_t)c * p.nsteps + hs) * NTTRACE + 80 + rel_t] = now;
                         }
                         if (!any) break;
+                        // nothing new in this trip: nap instead of spinning -- this warp shares a scheduler
+                        // with two consumer warps, and every tile waits for the slowest of the eight
+                        if (ready == last_ready) __nanosleep(60);
+                        last_ready = ready;
                     }
                 }
                 if (!live) break;
@@ -2604,7 +2609,12 @@ static int plan_geometry(b200l_ctx *c) {
             // consumer warps are done with it (row-major, up to 128 tiles); otherwise the lane that
             // finishes a row stores it to every peer itself (also forced by dbg bit 8)
             const int nt_plan = trans ? nt_t : (rows_max + TR - 1) / TR;
-            out->tile_sends = (c->world > 1 && !trans && nt_plan <= 128 && !(c->dbg & 256)) ? 1 : 0;
+            // (with a single peer the consumer lanes send their rows themselves: +1 % on 2 GPUs.  On 8 GPUs
+            // the sender warp wins even when a multicast mapping makes it one store per row -- measured per
+            // block step: sender warp + multimem 18.9 us, sender warp + 7 unicast stores 19.2, consumer lanes
+            // + multimem 20.2, consumer lanes + unicast 23.9)
+            const bool one_store = c->world == 2 && !(c->dbg & 512);
+            out->tile_sends = (c->world > 1 && !trans && nt_plan <= 128 && !(c->dbg & 256) && !one_store) ? 1 : 0;
         }
     };
     // the ring goes first (offset 0); sized after the fixed part is known
@@ -3008,10 +3018,10 @@ extern "C" int b200l_comm_attach(b200l_ctx *c, int32_t rank, int32_t world, void
         if (!peer_ptrs[r]) return fail("peer_ptrs[%d] is NULL", r);
     c->world = world;
     c->rank = rank;
-    c->geo_valid = 0;
-    if (plan_geometry(c)) { c->world = 1; c->rank = 0; c->geo_valid = 0; return 1; }
-    for (int r = 0; r < world; ++r) c->peer[r] = (ulonglong2 *)peer_ptrs[r];
     c->mc = (ulonglong2 *)mc_ptr;
+    c->geo_valid = 0;
+    if (plan_geometry(c)) { c->world = 1; c->rank = 0; c->mc = nullptr; c->geo_valid = 0; return 1; }
+    for (int r = 0; r < world; ++r) c->peer[r] = (ulonglong2 *)peer_ptrs[r];
     c->peer_ipc = 0;
     const size_t qw = (size_t)round_up(c->geo.rows_max_ + 2, 2);
     c->inbox_bytes = 2 * (size_t)c->grid * world * qw * 16;

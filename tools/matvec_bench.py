@@ -1,0 +1,84 @@
+#!/usr/bin/env python
+"""Roofline of the legacy mat-vec entry points (the step-wise path of ClassLassoCB_v1, of hooked
+subclasses and of DEBUG mode: gpu_calculation.py:264-292 in the reference) on C2 blocks:
+b200l_gemv_t_dev (g = A_m^T r) and b200l_gemv_n_dev (q = A_m d) on device vectors, CUDA events, cycling
+through all 100 blocks so that every call streams its 40 MB block from HBM (A = 4 GB >> L2), plus
+diag(A^T A) over the whole matrix (one pass).  Prints one JSON line.  GPU only."""
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    from bench import CONFIGS, make_device_instance, measured_peak
+    from convex_optimization_b200 import _lib
+    from convex_optimization_b200.gpu_calculation import GPU_Calculation
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--layout", default="row", choices=["row", "transposed"])
+    ap.add_argument("--dtype", default="float", choices=["float", "double"])
+    ap.add_argument("--reps", type=int, default=3)
+    args = ap.parse_args()
+    cfg = CONFIGS["c2"]
+    N, K, BLOCK = cfg["N"], cfg["K"], cfg["BLOCK"]
+    w = K // BLOCK
+    es = 4 if args.dtype == "float" else 8
+    dev = torch.device("cuda", 0)
+
+    class Cal(GPU_Calculation):
+        TYPE = args.dtype
+        LAYOUT = args.layout
+    ld = Cal.padded_ld(N, K, BLOCK)
+    tdt = torch.float32 if args.dtype == "float" else torch.float64
+    store, b, mu = make_device_instance(torch, dev, N, K, BLOCK, 0.01, 2, tdt, ld, args.layout)
+    cal = Cal.from_device_blocks(store, N, K, BLOCK)
+    stream = torch.cuda.current_stream(dev)
+    _lib.check(cal._lib.b200l_ctx_set_stream(cal.ctx, ctypes.c_void_p(stream.cuda_stream)))
+    r = torch.randn(max(N, cal.ld) + 64, dtype=torch.float64, device=dev)
+    d = torch.randn(w + 64, dtype=torch.float64, device=dev)
+    g = torch.empty(w + 64, dtype=torch.float64, device=dev)
+    q = torch.empty(N + 64, dtype=torch.float64, device=dev)
+    peak, src = measured_peak()
+    out = {"config": "C2 blocks: %s %dx%d per block, %s layout, 100 blocks cycled (HBM-resident)" % (args.dtype, N, w, args.layout),
+           "peak_GBs": peak, "peak_source": src, "block_bytes": N * w * es}
+
+    def timed(fn, ptr_in, ptr_out):
+        for m in range(BLOCK):
+            _lib.check(fn(cal.ctx, m, ctypes.c_void_p(ptr_in), ctypes.c_void_p(ptr_out)))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.reps):
+            for m in range(BLOCK):
+                _lib.check(fn(cal.ctx, m, ctypes.c_void_p(ptr_in), ctypes.c_void_p(ptr_out)))
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / (args.reps * BLOCK)
+        return {"us_per_call": us, "GBs": N * w * es / us / 1e3, "frac": N * w * es / us / 1e3 / peak}
+    out["gemv_t (A_m^T r)"] = timed(cal._lib.b200l_gemv_t_dev, r.data_ptr(), g.data_ptr())
+    out["gemv_n (A_m d)"] = timed(cal._lib.b200l_gemv_n_dev, d.data_ptr(), q.data_ptr())
+    # diag(A^T A): one pass over the whole matrix (re-bind to invalidate the cached diagonal)
+    dh = np.empty((BLOCK, w, 1))
+    ts = []
+    for _ in range(3):
+        _lib.check(cal._lib.b200l_ctx_bind_A(cal.ctx, ctypes.c_void_p(store.data_ptr())))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(cal._lib.b200l_diag_ata(cal.ctx, _lib.dptr(dh)))
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    out["diag_ATA (whole matrix, incl. D2H of K doubles)"] = {"ms": min(ts), "GBs": N * K * es / min(ts) / 1e6,
+                                                              "frac": N * K * es / min(ts) / 1e6 / peak}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -25,7 +25,11 @@ STALL = "smsp__average_warps_issue_stalled_"
 
 
 def full(rep, header):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    # either an .ncu-rep (exported here) or the CSV of `ncu -i X.ncu-rep --page raw --csv` made on the GPU box
+    if rep.endswith(".csv"):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     names, units, vals = rows[0], rows[1], rows[2]
     m = {n: (v, u) for n, u, v in zip(names, units, vals)}
