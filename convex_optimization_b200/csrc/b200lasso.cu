@@ -1679,7 +1679,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
 // ------------------------------------------------------------------------------------
 // part[y][chunk][col] = sum_{rows in chunk} A_y[row][col] * (SQ ? A_y[row][col] : vec[row]); blockIdx.y
 // selects one of several equally shaped matrices (the column blocks: diag(A^T A) of all blocks is
-// ONE launch)
+// ONE launch).  Thread = 16-byte column group, eight rows in flight per thread.
 template <typename T, bool SQ>
 __global__ void __launch_bounds__(256) colwsum_partial(const T *__restrict__ A, int64_t M, int ncols,
                                                        int64_t ld, const double *__restrict__ vec,
@@ -1687,6 +1687,7 @@ __global__ void __launch_bounds__(256) colwsum_partial(const T *__restrict__ A, 
                                                        int64_t mat_stride) {
     using VecT = typename VT<T>::type;
     constexpr int V = VT<T>::V;
+    constexpr int U = 8;
     const int chunk = blockIdx.x;
     A += (int64_t)blockIdx.y * mat_stride;
     part += (int64_t)blockIdx.y * gridDim.x * ncols;
@@ -1697,51 +1698,65 @@ __global__ void __launch_bounds__(256) colwsum_partial(const T *__restrict__ A, 
         double acc[V];
 #pragma unroll
         for (int e = 0; e < V; ++e) acc[e] = 0.0;
-#pragma unroll 4
-        for (int64_t r = r0; r < r1; ++r) {
-            const VecT v = __ldg(reinterpret_cast<const VecT *>(A + r * ld + (int64_t)cg * V));
-            const T *ve = reinterpret_cast<const T *>(&v);
-            if (SQ) {
+        const T *col = A + (int64_t)cg * V;
+        int64_t r = r0;
+        for (; r + U <= r1; r += U) {
+            VecT v[U];
+            double s[U];
 #pragma unroll
-                for (int e = 0; e < V; ++e) acc[e] += (double)ve[e] * (double)ve[e];
-            } else {
-                const double s = vec[r];
-#pragma unroll
-                for (int e = 0; e < V; ++e) acc[e] += (double)ve[e] * s;
+            for (int u = 0; u < U; ++u) {
+                v[u] = __ldg(reinterpret_cast<const VecT *>(col + (r + u) * ld));
+                s[u] = SQ ? 0.0 : __ldg(vec + r + u);
             }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const T *ve = reinterpret_cast<const T *>(&v[u]);
+#pragma unroll
+                for (int e = 0; e < V; ++e) acc[e] += (double)ve[e] * (SQ ? (double)ve[e] : s[u]);
+            }
+        }
+        for (; r < r1; ++r) {
+            const VecT v = __ldg(reinterpret_cast<const VecT *>(col + r * ld));
+            const T *ve = reinterpret_cast<const T *>(&v);
+            const double sc = SQ ? 0.0 : __ldg(vec + r);
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[e] += (double)ve[e] * (SQ ? (double)ve[e] : sc);
         }
 #pragma unroll
         for (int e = 0; e < V; ++e) part[(int64_t)chunk * ncols + cg * V + e] = acc[e];
     }
 }
 
-// out[y * out_stride + col] (+)= sum_chunk part[y][chunk][col], fixed order (deterministic):
-// 32 columns x 8 chunk groups per CTA, each thread adds every 8th chunk, thread row 0 adds the 8
+// out[y * out_stride + col] (+)= sum_chunk part[y][chunk][col] for col < ncols_out, fixed order
+// (deterministic): 8 columns x 32 chunk groups per CTA -- many small CTAs, the partials are a few MB --
+// each thread adds every 32nd chunk, then the 32 groups of a column are added in order
 __global__ void __launch_bounds__(256) reduce_partials(const double *__restrict__ part, int nchunks, int ncols,
-                                                       double *__restrict__ out, int accumulate, int64_t out_stride) {
-    __shared__ double sm[8][33];
-    const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
-    const int col = blockIdx.x * 32 + cx;
+                                                       double *__restrict__ out, int accumulate, int64_t out_stride,
+                                                       int ncols_out) {
+    __shared__ double sm[32][9];
+    const int cx = threadIdx.x & 7, gy = threadIdx.x >> 3;
+    const int col = blockIdx.x * 8 + cx;
     part += (int64_t)blockIdx.y * nchunks * ncols;
     double s = 0.0;
-    if (col < ncols) {
+    if (col < ncols_out) {
 #pragma unroll 4
-        for (int ch = gy; ch < nchunks; ch += 8) s += part[(int64_t)ch * ncols + col];
+        for (int ch = gy; ch < nchunks; ch += 32) s += part[(int64_t)ch * ncols + col];
     }
     sm[gy][cx] = s;
     __syncthreads();
-    if (gy == 0 && col < ncols) {
+    if (gy == 0 && col < ncols_out) {
         double t = 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t += sm[k][cx];
+        for (int k = 0; k < 32; ++k) t += sm[k][cx];
         double *o = out + (int64_t)blockIdx.y * out_stride + col;
         *o = accumulate ? *o + t : t;
     }
 }
 
-// out[row] (+)= sum_col A[row][col] * (SQ ? A[row][col] : vec[col]); one warp per row.  Rows are
-// written to out[(row / group) * out_stride + row % group] (group = rows per column block when
-// the rows of all blocks are processed in one launch)
+// out[row] (+)= sum_col A[row][col] * (SQ ? A[row][col] : vec[col]); one warp per row, eight 16-byte
+// loads in flight per lane (a C2 row in one round trip; two in flight were latency-bound: 2.1 TB/s).  Rows are written to
+// out[(row / group) * out_stride + row % group] (group = rows per column block when the rows of
+// all blocks are processed in one launch)
 template <typename T, bool SQ>
 __global__ void __launch_bounds__(256) rowdot_kernel(const T *__restrict__ A, int64_t M, int ncols,
                                                      int64_t ld, const double *__restrict__ vec,
@@ -1749,34 +1764,38 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const T *__restrict__ A, in
                                                      int64_t out_stride) {
     using VecT = typename VT<T>::type;
     constexpr int V = VT<T>::V;
+    constexpr int U = 8;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int ncg = ncols / V;
     for (int64_t r = warp; r < M; r += nwarps) {
-        double acc0 = 0.0, acc1 = 0.0;
-        int cg = lane;
-        for (; cg + 32 < ncg; cg += 64) {                // two independent 16-byte loads per trip
-            const VecT v = __ldg(reinterpret_cast<const VecT *>(A + r * ld + (int64_t)cg * V));
-            const VecT u = __ldg(reinterpret_cast<const VecT *>(A + r * ld + (int64_t)(cg + 32) * V));
-            const T *ve = reinterpret_cast<const T *>(&v);
-            const T *ue = reinterpret_cast<const T *>(&u);
+        const T *row = A + r * ld;
+        double acc[U];
 #pragma unroll
-            for (int e = 0; e < V; ++e) {
-                acc0 += (double)ve[e] * (SQ ? (double)ve[e] : vec[cg * V + e]);
-                acc1 += (double)ue[e] * (SQ ? (double)ue[e] : vec[(cg + 32) * V + e]);
+        for (int u = 0; u < U; ++u) acc[u] = 0.0;
+        for (int cg0 = lane; cg0 < ncg; cg0 += 32 * U) {
+            VecT v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int cg = cg0 + 32 * u;
+                if (cg < ncg) v[u] = __ldg(reinterpret_cast<const VecT *>(row + (int64_t)cg * V));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int cg = cg0 + 32 * u;
+                if (cg < ncg) {
+                    const T *ve = reinterpret_cast<const T *>(&v[u]);
+#pragma unroll
+                    for (int e = 0; e < V; ++e)
+                        acc[u] += (double)ve[e] * (SQ ? (double)ve[e] : __ldg(vec + cg * V + e));
+                }
             }
         }
-        if (cg < ncg) {
-            const VecT v = __ldg(reinterpret_cast<const VecT *>(A + r * ld + (int64_t)cg * V));
-            const T *ve = reinterpret_cast<const T *>(&v);
-#pragma unroll
-            for (int e = 0; e < V; ++e) acc0 += (double)ve[e] * (SQ ? (double)ve[e] : vec[cg * V + e]);
-        }
-        const double acc = warp_sum(acc0 + acc1);
+        const double total = warp_sum(((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7])));
         if (lane == 0) {
             double *o = out + (r / group) * out_stride + r % group;
-            *o = accumulate ? *o + acc : acc;
+            *o = accumulate ? *o + total : total;
         }
     }
 }
@@ -2120,22 +2139,26 @@ extern "C" int b200l_ctx_bind_A(b200l_ctx *c, const void *A_dev) {
 // ------------------------------------------------------------------------------------
 // device-level mat-vecs on block m (vectors are device doubles)
 // ------------------------------------------------------------------------------------
-// nmat equally shaped matrices (stride mat_stride elements), results out[y * out_stride + col]
+// nmat equally shaped matrices (stride mat_stride elements), results out[y * out_stride + col], col < ncols_out
 template <typename T>
 static int colwsum_dev(b200l_ctx *c, const T *Ablk, int64_t M, int ncols, int64_t ld, const double *vec,
                        double *out, bool sq, int accumulate, int nmat = 1, int64_t mat_stride = 0,
-                       int64_t out_stride = 0) {
-    const int budget = std::max(1, c->part_chunks / nmat);
-    int chunks = (int)std::min<int64_t>(budget, M);
+                       int64_t out_stride = 0, int ncols_out = -1) {
+    // chunks of rows: enough CTAs to fill the machine (a CTA is 256 threads, eight loads in flight each), few
+    // partials: two per SM for one block, four per SM over all blocks of the one-pass diag(A^T A)
+    const int budget = std::max(1, (nmat > 1 ? 4 : 2) * c->sm_count / nmat);
+    int chunks = (int)std::min<int64_t>(budget, (M + 7) / 8);
+    chunks = std::max(chunks, 1);
     int rpc = (int)((M + chunks - 1) / chunks);
     chunks = (int)((M + rpc - 1) / rpc);
+    if (ncols_out < 0) ncols_out = ncols;
     const dim3 grid(chunks, nmat);
     if (sq)
         colwsum_partial<T, true><<<grid, 256, 0, c->stream>>>(Ablk, M, ncols, ld, vec, c->part, rpc, mat_stride);
     else
         colwsum_partial<T, false><<<grid, 256, 0, c->stream>>>(Ablk, M, ncols, ld, vec, c->part, rpc, mat_stride);
-    reduce_partials<<<dim3((ncols + 31) / 32, nmat), 256, 0, c->stream>>>(c->part, chunks, ncols, out, accumulate,
-                                                                          out_stride);
+    reduce_partials<<<dim3((ncols_out + 7) / 8, nmat), 256, 0, c->stream>>>(c->part, chunks, ncols, out, accumulate,
+                                                                           out_stride, ncols_out);
     CK(cudaGetLastError());
     return 0;
 }
@@ -2158,8 +2181,8 @@ static int rowdot_dev(b200l_ctx *c, const T *Ablk, int64_t M, int ncols, int64_t
 template <typename T>
 static int gemv_t_dev(b200l_ctx *c, int m, const double *r, double *g) {
     const T *Ablk = reinterpret_cast<const T *>(c->A) + (int64_t)m * c->brows * c->ld;
-    if (c->layout == B200L_ROWMAJOR)
-        return colwsum_dev<T>(c, Ablk, c->N, (int)c->ld, c->ld, r, g, false, 0);
+    if (c->layout == B200L_ROWMAJOR)        // only the w real columns are written (g may hold exactly w entries)
+        return colwsum_dev<T>(c, Ablk, c->N, (int)c->ld, c->ld, r, g, false, 0, 1, 0, 0, c->w);
     return rowdot_dev<T>(c, Ablk, c->w, (int)c->ld, c->ld, r, g, false, 0);
 }
 // q[N] (+)= A_m d[xld]
@@ -2168,7 +2191,8 @@ static int gemv_n_dev(b200l_ctx *c, int m, const double *dvec, double *q, int ac
     const T *Ablk = reinterpret_cast<const T *>(c->A) + (int64_t)m * c->brows * c->ld;
     if (c->layout == B200L_ROWMAJOR)
         return rowdot_dev<T>(c, Ablk, c->N, (int)c->ld, c->ld, dvec, q, false, accumulate);
-    return colwsum_dev<T>(c, Ablk, c->w, (int)c->ld, c->ld, dvec, q, false, accumulate);
+    // (the pre-transposed block has ld >= N padded entries per column: only the N real ones are written)
+    return colwsum_dev<T>(c, Ablk, c->w, (int)c->ld, c->ld, dvec, q, false, accumulate, 1, 0, 0, (int)c->N);
 }
 
 static int need_A(b200l_ctx *c) {
@@ -2264,10 +2288,7 @@ extern "C" int b200l_gemv_t_dev(b200l_ctx *c, int32_t m, const double *r_dev, do
         CK(cudaMemcpyAsync(c->vin, r_dev, (size_t)c->N * 8, cudaMemcpyDeviceToDevice, c->stream));
         rin = c->vin;
     }
-    int rc = c->dtype == B200L_F32 ? gemv_t_dev<float>(c, m, rin, c->vout) : gemv_t_dev<double>(c, m, rin, c->vout);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(g_dev, c->vout, (size_t)c->w * 8, cudaMemcpyDeviceToDevice, c->stream));
-    return 0;
+    return c->dtype == B200L_F32 ? gemv_t_dev<float>(c, m, rin, g_dev) : gemv_t_dev<double>(c, m, rin, g_dev);
 }
 
 extern "C" int b200l_gemv_n_dev(b200l_ctx *c, int32_t m, const double *d_dev, double *q_dev) {
@@ -2281,10 +2302,7 @@ extern "C" int b200l_gemv_n_dev(b200l_ctx *c, int32_t m, const double *d_dev, do
         CK(cudaMemcpyAsync(c->vin, d_dev, (size_t)c->w * 8, cudaMemcpyDeviceToDevice, c->stream));
         din = c->vin;
     }
-    int rc = c->dtype == B200L_F32 ? gemv_n_dev<float>(c, m, din, c->vout, 0) : gemv_n_dev<double>(c, m, din, c->vout, 0);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(q_dev, c->vout, (size_t)c->N * 8, cudaMemcpyDeviceToDevice, c->stream));
-    return 0;
+    return c->dtype == B200L_F32 ? gemv_n_dev<float>(c, m, din, q_dev, 0) : gemv_n_dev<double>(c, m, din, q_dev, 0);
 }
 
 // ------------------------------------------------------------------------------------

@@ -50,18 +50,45 @@ def main():
            "peak_GBs": peak, "peak_source": src, "block_bytes": N * w * es}
 
     def timed(fn, ptr_in, ptr_out):
-        for m in range(BLOCK):
-            _lib.check(fn(cal.ctx, m, ctypes.c_void_p(ptr_in), ctypes.c_void_p(ptr_out)))
+        def sweep():
+            for m in range(BLOCK):
+                _lib.check(fn(cal.ctx, m, ctypes.c_void_p(ptr_in), ctypes.c_void_p(ptr_out)))
+        sweep()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.reps):
-            for m in range(BLOCK):
-                _lib.check(fn(cal.ctx, m, ctypes.c_void_p(ptr_in), ctypes.c_void_p(ptr_out)))
+            sweep()
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / (args.reps * BLOCK)
-        return {"us_per_call": us, "GBs": N * w * es / us / 1e3, "frac": N * w * es / us / 1e3 / peak}
+        rec = {"us_per_call_from_python": us, "GBs_from_python": N * w * es / us / 1e3,
+               "note": "one ctypes call per block from a Python loop: the host issues a call every ~15 us, the GPU idles in between"}
+        # the same 100 calls captured once in a CUDA graph and replayed: device time of the kernels themselves
+        try:
+            side = torch.cuda.Stream()
+            _lib.check(cal._lib.b200l_ctx_set_stream(cal.ctx, ctypes.c_void_p(side.cuda_stream)))
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                sweep()
+                side.synchronize()
+                with torch.cuda.graph(graph, stream=side):
+                    sweep()
+            graph.replay()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(args.reps):
+                graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            usg = e0.elapsed_time(e1) * 1e3 / (args.reps * BLOCK)
+            rec.update({"us_per_call": usg, "GBs": N * w * es / usg / 1e3, "frac": N * w * es / usg / 1e3 / peak,
+                        "how": "100 calls (one per block) captured in a CUDA graph, replayed %d times" % args.reps})
+        except Exception as e:
+            rec["graph"] = "capture failed: %r" % (e,)
+        finally:
+            _lib.check(cal._lib.b200l_ctx_set_stream(cal.ctx, ctypes.c_void_p(stream.cuda_stream)))
+        return rec
     out["gemv_t (A_m^T r)"] = timed(cal._lib.b200l_gemv_t_dev, r.data_ptr(), g.data_ptr())
     out["gemv_n (A_m d)"] = timed(cal._lib.b200l_gemv_n_dev, d.data_ptr(), q.data_ptr())
     # diag(A^T A): one pass over the whole matrix (re-bind to invalidate the cached diagonal)
