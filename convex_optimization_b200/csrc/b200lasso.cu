@@ -1753,49 +1753,385 @@ __global__ void __launch_bounds__(256) reduce_partials(const double *__restrict_
     }
 }
 
-// out[row] (+)= sum_col A[row][col] * (SQ ? A[row][col] : vec[col]); one warp per row, eight 16-byte
-// loads in flight per lane (a C2 row in one round trip; two in flight were latency-bound: 2.1 TB/s).  Rows are written to
-// out[(row / group) * out_stride + row % group] (group = rows per column block when the rows of
-// all blocks are processed in one launch)
-template <typename T, bool SQ>
-__global__ void __launch_bounds__(256) rowdot_kernel(const T *__restrict__ A, int64_t M, int ncols,
-                                                     int64_t ld, const double *__restrict__ vec,
-                                                     double *__restrict__ out, int accumulate, int64_t group,
-                                                     int64_t out_stride) {
+// out[col] (+)= sum_row A[row][col] * vec[row] for ONE matrix in ONE launch (the step-wise A_m^T r of the
+// row-major layout, A_m d of the pre-transposed one).  Grid = (RC row chunks) x (column slabs of 256 16-byte
+// groups), launched cooperatively when RC > 1 so that all CTAs are co-resident.  A CTA is 4 row sub-groups x 256
+// column groups, eight rows in flight per thread; its partial sums go out as self-validating 16-byte words
+// (value, launch number) -- the exchange of the fused kernel, no fence, no flag, no second launch -- and the RC
+// CTAs of a slab each add up a share of the slab's columns: warp per column, lane = chunk, fixed order,
+// fixed shuffle tree (deterministic).
+constexpr int CW_THREADS = 1024;
+constexpr int CW_CG = 256;
+constexpr int CW_SUB = CW_THREADS / CW_CG;
+constexpr int CW_MAXP = 8;         // chunks per lane in the gather: RC <= 32 * CW_MAXP
+
+// partial sums of a chunk -> exchange words -> my share of the slab's columns (colwsum_fused, matvec_stream)
+template <int SL>
+__device__ __forceinline__ void cw_exchange(double mine, int c_l, int nthreads, int RC, int i, int j,
+                                            ulonglong2 *words, unsigned long long seq, double *out, int accumulate,
+                                            int ncols_out) {
+    if (RC == 1) {
+        const int colg = j * SL + c_l;
+        if (c_l < SL && colg < ncols_out) out[colg] = accumulate ? out[colg] + mine : mine;
+        return;
+    }
+    if (c_l < SL) ll_st(words + (size_t)(j * RC + i) * SL + c_l, (unsigned long long)__double_as_longlong(mine), seq);
+    const int c_lo = (int)((int64_t)SL * i / RC), c_hi = (int)((int64_t)SL * (i + 1) / RC);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned long long t_start = globaltimer_ns();
+    for (int cc = c_lo + warp; cc < c_hi; cc += nthreads / 32) {
+        const int colg = j * SL + cc;
+        if (colg >= ncols_out) break;
+        const ulonglong2 *src = words + (size_t)j * RC * SL + cc;
+        ulonglong2 w[CW_MAXP];
+#pragma unroll
+        for (int k = 0; k < CW_MAXP; ++k)
+            if (lane + 32 * k < RC) w[k] = ll_ld(src + (size_t)(lane + 32 * k) * SL);
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < CW_MAXP; ++k) {
+            if (lane + 32 * k < RC) {
+                unsigned spin = 0;
+                while (w[k].y != seq) {
+                    if ((++spin & 1023u) == 0u && globaltimer_ns() - t_start > 4000000000ULL) __trap();
+                    w[k] = ll_ld(src + (size_t)(lane + 32 * k) * SL);
+                }
+                sum += __longlong_as_double((long long)w[k].x);
+            }
+        }
+        sum = warp_sum(sum);
+        if (lane == 0) out[colg] = accumulate ? out[colg] + sum : sum;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CW_THREADS, 1) colwsum_fused(const T *__restrict__ A, int64_t M, int ncols,
+                                                               int64_t ld, const double *__restrict__ vec,
+                                                               ulonglong2 *words, unsigned long long seq,
+                                                               double *out, int accumulate, int ncols_out) {
     using VecT = typename VT<T>::type;
     constexpr int V = VT<T>::V;
     constexpr int U = 8;
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int ncg = ncols / V;
-    for (int64_t r = warp; r < M; r += nwarps) {
-        const T *row = A + r * ld;
-        double acc[U];
+    constexpr int SL = CW_CG * V;                 // columns of a slab
+    __shared__ double red[CW_SUB][V][CW_CG];
+    const int RC = gridDim.x, i = blockIdx.x, j = blockIdx.y;
+    const int tid = threadIdx.x, cgl = tid & (CW_CG - 1), sub = tid / CW_CG;
+    const int ncg = ncols / V;                    // ncols is a multiple of V (padded)
+    const int cg = j * CW_CG + cgl;
+    const int64_t r0 = M * i / RC, r1 = M * (i + 1) / RC;
+    double acc[V];
 #pragma unroll
-        for (int u = 0; u < U; ++u) acc[u] = 0.0;
-        for (int cg0 = lane; cg0 < ncg; cg0 += 32 * U) {
+    for (int e = 0; e < V; ++e) acc[e] = 0.0;
+    if (cg < ncg) {
+        const T *col = A + (int64_t)cg * V;
+        int64_t r = r0 + sub;                     // the sub-groups take adjacent rows (one DRAM page)
+        for (; r + (U - 1) * CW_SUB < r1; r += U * CW_SUB) {
             VecT v[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int cg = cg0 + 32 * u;
-                if (cg < ncg) v[u] = __ldg(reinterpret_cast<const VecT *>(row + (int64_t)cg * V));
-            }
+            for (int u = 0; u < U; ++u) v[u] = __ldg(reinterpret_cast<const VecT *>(col + (r + u * CW_SUB) * ld));
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int cg = cg0 + 32 * u;
-                if (cg < ncg) {
-                    const T *ve = reinterpret_cast<const T *>(&v[u]);
+                const double sc = __ldg(vec + r + u * CW_SUB);
+                const T *ve = reinterpret_cast<const T *>(&v[u]);
 #pragma unroll
-                    for (int e = 0; e < V; ++e)
-                        acc[u] += (double)ve[e] * (SQ ? (double)ve[e] : __ldg(vec + cg * V + e));
-                }
+                for (int e = 0; e < V; ++e) acc[e] += (double)ve[e] * sc;
             }
         }
-        const double total = warp_sum(((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7])));
-        if (lane == 0) {
-            double *o = out + (r / group) * out_stride + r % group;
-            *o = accumulate ? *o + total : total;
+        for (; r < r1; r += CW_SUB) {
+            const VecT v = __ldg(reinterpret_cast<const VecT *>(col + r * ld));
+            const double sc = __ldg(vec + r);
+            const T *ve = reinterpret_cast<const T *>(&v);
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[e] += (double)ve[e] * sc;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < V; ++e) red[sub][e][cgl] = acc[e];
+    __syncthreads();
+    // the CTA's partial of column c_l of the slab: sub-groups added in order
+    double mine = 0.0;
+    const int c_l = tid;
+    if (c_l < SL) {
+        const int g = c_l / V, e = c_l % V;
+        mine = ((red[0][e][g] + red[1][e][g]) + red[2][e][g]) + red[3][e][g];
+    }
+    cw_exchange<SL>(mine, c_l, CW_THREADS, RC, i, j, words, seq, out, accumulate, ncols_out);
+}
+
+// ------------------------------------------------------------------------------------
+// TMA-streamed row dots of ONE matrix (the step-wise path on blocks that fill the machine)
+// ------------------------------------------------------------------------------------
+// out[row] (+)= A[row][:] . vec, one CTA per SM: a producer warp streams the CTA's rows -- tiles of TR rows x one
+// column slab, one bulk copy per tile when the slab is the whole row, else one per row -- through a ring of S
+// shared-memory slots (mbarrier full/empty pairs); 8 consumer warps work from shared memory.  The bytes in
+// flight (the whole ring, 150-220 KB per SM) no longer depend on registers, which the load-batch kernel below
+// cannot offer: measured on C2 blocks 11.0 us per 40 MB block against 14.2 us.  (Column sums stay with
+// colwsum_fused: their cross-CTA exchange, not the stream, is what is left of their time; a streamed variant
+// measured 13.6 us against 12.3 us.)
+//   short rows: the warp that owns a row (rows round-robin over the warps) walks its slabs and keeps its sum;
+//               VREG: the row is one batch of the warp and its part of vec stays in registers, else vec sits
+//               in shared memory, split in two arrays so that 16-byte reads are conflict-free;
+//   long rows (one row per tile, `coop`): every warp takes an eighth of each tile, the warps' sums of a row are
+//               added in order through shared memory.
+constexpr int MS_NW = 8;
+constexpr int MS_NTC = MS_NW * 32;
+constexpr int MS_THREADS = MS_NTC + 32;
+constexpr int MS_MAXS = 16;
+
+struct MsParams {
+    const void *A;
+    int64_t M, ld;
+    int ncols;                     // multiple of V
+    const double *vec;
+    double *out;
+    int accumulate;
+    int RC, ncs, SG;               // row chunks (= grid), column slabs, 16-byte groups per slab
+    int TR, S, slot_bytes, contig, coop;
+    int off_vec, off_part, off_ring;   // shared memory: barriers at 0, vec, the warps' sums of a shared row, ring
+};
+
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
+    unsigned spin = 0;
+    unsigned long long t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spin & 255u) == 0u) {            // (a lost copy must not hang the GPU)
+            const unsigned long long now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ULL) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void ms_cbar() { asm volatile("bar.sync 2, %0;" ::"n"(MS_NTC) : "memory"); }
+
+template <typename T, bool VREG>
+__global__ void __launch_bounds__(MS_THREADS, 1) rowdot_stream(const MsParams p) {
+    using VecT = typename VT<T>::type;
+    constexpr int V = VT<T>::V;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *empty = full + MS_MAXS;
+    unsigned char *ring = smem + p.off_ring;
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int i = blockIdx.x;
+    const int ncg = p.ncols / V;
+    const int64_t r0 = p.M * i / p.RC, r1 = p.M * (i + 1) / p.RC;
+    const int nrg = (int)((r1 - r0 + p.TR - 1) / p.TR);          // row groups of this CTA
+    const T *A = reinterpret_cast<const T *>(p.A);
+    if (tid == 0) {
+        for (int s = 0; s < p.S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, MS_NW); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (wid == MS_NW) {
+        // ---- producer warp
+        int slot = 0;
+        uint32_t ph = 1;
+        for (int g = 0; g < nrg; ++g) {
+            const int64_t rk0 = r0 + (int64_t)g * p.TR;
+            const int nrows = (int)min((int64_t)p.TR, r1 - rk0);
+            for (int j = 0; j < p.ncs; ++j) {
+                const int sg = min(p.SG, ncg - j * p.SG);         // groups of this slab
+                const uint32_t sb = (uint32_t)sg * 16u;
+                mbar_wait_bounded(empty + slot, ph);
+                unsigned char *dst = ring + (size_t)slot * p.slot_bytes;
+                const T *src = A + rk0 * p.ld + (int64_t)j * p.SG * V;
+                if (p.contig) {
+                    if (lane == 0) {
+                        mbar_expect_tx(full + slot, sb * (uint32_t)nrows);
+                        tma_bulk_g2s(dst, src, sb * (uint32_t)nrows, full + slot);
+                    }
+                } else {
+                    if (lane == 0) mbar_expect_tx(full + slot, sb * (uint32_t)nrows);
+                    __syncwarp();
+                    if (lane < nrows) tma_bulk_g2s(dst + (size_t)lane * sb, src + (int64_t)lane * p.ld, sb, full + slot);
+                }
+                if (++slot == p.S) { slot = 0; ph ^= 1u; }
+            }
+        }
+        return;
+    }
+    // ---- consumers
+    int slot = 0;
+    uint32_t ph = 0;
+    double vr[VREG ? 8 * V : 1];
+    double2 *vlo = reinterpret_cast<double2 *>(smem + p.off_vec), *vhi = vlo + ncg;
+    if (VREG) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int cg = lane + 32 * u;
+#pragma unroll
+            for (int e = 0; e < V; ++e) vr[u * V + e] = cg < ncg ? __ldg(p.vec + (int64_t)cg * V + e) : 0.0;
+        }
+    } else {
+        for (int cg = tid; cg < ncg; cg += MS_NTC) {
+            vlo[cg] = make_double2(__ldg(p.vec + (int64_t)cg * V), __ldg(p.vec + (int64_t)cg * V + 1));
+            if (V == 4) vhi[cg] = make_double2(__ldg(p.vec + (int64_t)cg * V + 2), __ldg(p.vec + (int64_t)cg * V + 3));
+        }
+        ms_cbar();
+    }
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    // one 16-byte group of the row against its part of vec in shared memory
+    auto fma_group = [&](const unsigned char *gp, int cg) {
+        const VecT v = *reinterpret_cast<const VecT *>(gp);
+        const T *ve = reinterpret_cast<const T *>(&v);
+        const double2 lo = vlo[cg];
+        acc[0] += (double)ve[0] * lo.x;
+        acc[1] += (double)ve[1] * lo.y;
+        if (V == 4) {
+            const double2 hi = vhi[cg];
+            acc[2] += (double)ve[V == 4 ? 2 : 0] * hi.x;
+            acc[3] += (double)ve[V == 4 ? 3 : 0] * hi.y;
+        }
+    };
+    if (!VREG && p.coop) {
+        double *part = reinterpret_cast<double *>(smem + p.off_part);     // [2][MS_NW], one barrier per row
+        for (int g = 0; g < nrg; ++g) {
+            for (int j = 0; j < p.ncs; ++j) {
+                const int sg = min(p.SG, ncg - j * p.SG);
+                mbar_wait_bounded(full + slot, ph);
+                const unsigned char *row = ring + (size_t)slot * p.slot_bytes;
+#pragma unroll 4
+                for (int c = tid; c < sg; c += MS_NTC) fma_group(row + (size_t)c * 16, j * p.SG + c);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + slot);
+                if (++slot == p.S) { slot = 0; ph ^= 1u; }
+            }
+            const double total = warp_sum((acc[0] + acc[1]) + (acc[2] + acc[3]));
+            acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
+            if (lane == 0) part[(g & 1) * MS_NW + wid] = total;
+            ms_cbar();
+            if (tid == 0) {
+                double t = 0.0;
+#pragma unroll
+                for (int k = 0; k < MS_NW; ++k) t += part[(g & 1) * MS_NW + k];
+                double *o = p.out + r0 + g;
+                *o = p.accumulate ? *o + t : t;
+            }
+        }
+        return;
+    }
+    for (int g = 0; g < nrg; ++g) {
+        const int64_t rk0 = r0 + (int64_t)g * p.TR;
+        const int nrows = (int)min((int64_t)p.TR, r1 - rk0);
+        // my row of this group (TR <= MS_NW: at most one)
+        const int l = (wid - (int)(((int64_t)g * p.TR) % MS_NW) + MS_NW) % MS_NW;
+        const bool mine = l < nrows;
+        for (int j = 0; j < p.ncs; ++j) {
+            const int sg = min(p.SG, ncg - j * p.SG);
+            mbar_wait_bounded(full + slot, ph);
+            if (mine) {
+                const unsigned char *row = ring + (size_t)slot * p.slot_bytes + (size_t)l * sg * 16;
+                if (VREG) {
+                    VecT v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (lane + 32 * u < sg) v[u] = *reinterpret_cast<const VecT *>(row + (size_t)(lane + 32 * u) * 16);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (lane + 32 * u < sg) {
+                            const T *ve = reinterpret_cast<const T *>(&v[u]);
+#pragma unroll
+                            for (int e = 0; e < V; ++e) acc[u & 3] += (double)ve[e] * vr[VREG ? u * V + e : 0];
+                        }
+                    }
+                } else {
+#pragma unroll 4
+                    for (int c = lane; c < sg; c += 32) fma_group(row + (size_t)c * 16, j * p.SG + c);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + slot);
+            if (++slot == p.S) { slot = 0; ph ^= 1u; }
+        }
+        if (mine) {
+            const double total = warp_sum((acc[0] + acc[1]) + (acc[2] + acc[3]));
+            if (lane == 0) {
+                double *o = p.out + rk0 + l;
+                *o = p.accumulate ? *o + total : total;
+            }
+            acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
+        }
+    }
+}
+
+// out[row] (+)= sum_col A[row][col] * (SQ ? A[row][col] : vec[col]).  WPR warps of a CTA share a row (each a
+// contiguous range of 16-byte column groups; their sums are added in order through shared memory), eight
+// 16-byte loads in flight per lane; at any time the grid works on a contiguous window of rows.  VREG: a warp's
+// range is one batch (a C2 row on one warp), its part of vec stays in registers for all its rows.  Rows are
+// written to out[(row / group) * out_stride + row % group] (group = rows per column block when the rows
+// of all blocks are processed in one launch).
+template <typename T, bool SQ, bool VREG>
+__global__ void __launch_bounds__(256, 2) rowdot_kernel(const T *__restrict__ A, int64_t M, int ncols,
+                                                        int64_t ld, const double *__restrict__ vec,
+                                                        double *__restrict__ out, int accumulate, int64_t group,
+                                                        int64_t out_stride, int wpr) {
+    using VecT = typename VT<T>::type;
+    constexpr int V = VT<T>::V;
+    constexpr int U = 8;
+    __shared__ double sm[2][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ncg = ncols / V;
+    const int rpc = 8 / wpr;                       // rows of a CTA per trip
+    const int seg = warp % wpr, rslot = warp / wpr;
+    const int gper = (ncg + wpr - 1) / wpr;
+    const int g0 = seg * gper, g1 = min(ncg, g0 + gper);
+    double vr[VREG && !SQ ? U * V : 1];
+    if (VREG && !SQ) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int cg = g0 + lane + 32 * u;
+#pragma unroll
+            for (int e = 0; e < V; ++e) vr[u * V + e] = cg < g1 ? __ldg(vec + (int64_t)cg * V + e) : 0.0;
+        }
+    }
+    const int64_t stride = (int64_t)gridDim.x * rpc;
+    const int64_t ntrips = (M + stride - 1) / stride;
+    for (int64_t trip = 0; trip < ntrips; ++trip) {
+        const int64_t rbase = trip * stride + (int64_t)blockIdx.x * rpc;
+        const int64_t r = rbase + rslot;
+        double total = 0.0;
+        if (r < M) {
+            const T *row = A + r * ld;
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int c0 = g0 + lane; c0 < g1; c0 += 32 * U) {
+                VecT v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int cg = c0 + 32 * u;
+                    if (cg < g1) v[u] = __ldg(reinterpret_cast<const VecT *>(row + (int64_t)cg * V));
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int cg = c0 + 32 * u;
+                    if (cg < g1) {
+                        const T *ve = reinterpret_cast<const T *>(&v[u]);
+#pragma unroll
+                        for (int e = 0; e < V; ++e) {
+                            const double m = SQ ? (double)ve[e]
+                                                : (VREG ? vr[(VREG && !SQ ? u * V + e : 0)] : __ldg(vec + (int64_t)cg * V + e));
+                            acc[u & 3] += (double)ve[e] * m;
+                        }
+                    }
+                }
+                if (VREG) break;
+            }
+            total = warp_sum((acc[0] + acc[1]) + (acc[2] + acc[3]));
+        }
+        if (wpr == 1) {
+            if (r < M && lane == 0) {
+                double *o = out + (r / group) * out_stride + r % group;
+                *o = accumulate ? *o + total : total;
+            }
+        } else {
+            if (lane == 0) sm[trip & 1][warp] = total;
+            __syncthreads();
+            const int64_t rr = rbase + threadIdx.x;
+            if ((int)threadIdx.x < rpc && rr < M) {
+                double t = 0.0;
+                for (int k = 0; k < wpr; ++k) t += sm[trip & 1][threadIdx.x * wpr + k];
+                double *o = out + (rr / group) * out_stride + rr % group;
+                *o = accumulate ? *o + t : t;
+            }
         }
     }
 }
@@ -1946,6 +2282,9 @@ struct b200l_ctx {
     // scratch
     double *vin, *vout, *part;
     int part_chunks;
+    ulonglong2 *cw_words;         // exchange words of colwsum_fused: one slab of partials per CTA
+    unsigned long long cw_seq;    // launches of colwsum_fused so far (the tag of their words)
+    int cw_occ, ms_ready;
     // cross-CTA exchange buffers of the fused kernel (LL words, see above)
     ulonglong2 *gLL, *dLL, *sLL;
     size_t gLL_bytes;
@@ -2071,6 +2410,7 @@ extern "C" int b200l_ctx_create(b200l_ctx **out, int dtype, int layout, int64_t 
     ALLOC(c->vin, vmax * 8);
     ALLOC(c->vout, vmax * 8);
     ALLOC(c->part, (int64_t)c->part_chunks * part_cols * 8);
+    ALLOC(c->cw_words, (int64_t)c->sm_count * CW_CG * 4 * 16);
     ALLOC(c->dLL, (c->xld + 2 * GMAX + 2) * 16);
     ALLOC(c->sLL, GMAX * 4 * 16);
     ALLOC(c->abort_flag, 64);
@@ -2084,6 +2424,7 @@ extern "C" int b200l_ctx_create(b200l_ctx **out, int dtype, int layout, int64_t 
     CK(cudaMemset(c->r, 0, npad * 8));
     CK(cudaMemset(c->b, 0, npad * 8));
     CK(cudaMemset(c->gamma_state, 0, 8));
+    CK(cudaMemset(c->cw_words, 0, (size_t)c->sm_count * CW_CG * 4 * 16));
     CK(cudaMemset(c->state, 0, 64));
     CK(cudaMemset(c->dLL, 0, (size_t)(c->xld + 2 * GMAX + 2) * 16));
     CK(cudaMemset(c->sLL, 0, (size_t)GMAX * 4 * 16));
@@ -2099,7 +2440,7 @@ extern "C" int b200l_ctx_destroy(b200l_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     comm_release(c);
-    void *ptrs[] = {c->x, c->d, c->drec, c->dsum, c->r, c->b, c->vin, c->vout, c->part, c->gLL,
+    void *ptrs[] = {c->x, c->d, c->drec, c->dsum, c->r, c->b, c->vin, c->vout, c->part, c->cw_words, c->gLL,
                     c->dLL, c->sLL, c->abort_flag, c->gamma_state, c->objbuf, c->state, c->err_hist,
                     c->time_hist, c->trace, c->ttrace, c->order};
     for (void *p : ptrs)
@@ -2163,17 +2504,98 @@ static int colwsum_dev(b200l_ctx *c, const T *Ablk, int64_t M, int ncols, int64_
     return 0;
 }
 
+// one matrix, one launch (colwsum_fused): the exchange words of the chunks live in c->cw_words
+template <typename T>
+static int colwsum_one(b200l_ctx *c, const T *Ablk, int64_t M, int ncols, int64_t ld, const double *vec,
+                       double *out, int accumulate, int ncols_out) {
+    constexpr int V = VT<T>::V;
+    const int ncg = ncols / V;
+    const int ncs = (ncg + CW_CG - 1) / CW_CG;
+    if (!c->cw_occ) {
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)colwsum_fused<T>, CW_THREADS, 0));
+        if (occ < 1) return fail("internal: colwsum_fused does not fit on an SM");
+        c->cw_occ = occ;
+    }
+    // row chunks: as many CTAs as SMs, at least 32 rows (one batch of every sub-group) per chunk
+    int64_t rc = std::min<int64_t>(c->sm_count / std::max(ncs, 1), (M + 31) / 32);
+    rc = std::max<int64_t>(1, std::min<int64_t>(rc, 32 * CW_MAXP));
+    int RC = (int)rc;
+    const unsigned long long seq = ++c->cw_seq;
+    void *args[] = {(void *)&Ablk, (void *)&M, (void *)&ncols, (void *)&ld, (void *)&vec, (void *)&c->cw_words,
+                    (void *)&seq, (void *)&out, (void *)&accumulate, (void *)&ncols_out};
+    if (RC > 1)
+        CK(cudaLaunchCooperativeKernel((const void *)colwsum_fused<T>, dim3(RC, ncs), dim3(CW_THREADS), args, 0,
+                                       c->stream));
+    else
+        CK(cudaLaunchKernel((const void *)colwsum_fused<T>, dim3(1, ncs), dim3(CW_THREADS), args, 0, c->stream));
+    return 0;
+}
+
 template <typename T>
 static int rowdot_dev(b200l_ctx *c, const T *Ablk, int64_t M, int ncols, int64_t ld, const double *vec,
                       double *out, bool sq, int accumulate, int64_t group = 0, int64_t out_stride = 0) {
-    const int64_t warps = std::min<int64_t>(M, (int64_t)c->sm_count * 64);
-    const int blocks = (int)((warps + 7) / 8);
+    constexpr int V = VT<T>::V;
+    const int ncg = ncols / V;
+    // two CTAs of eight warps per SM; short matrices: several warps per row until most warps have one
+    const int blocks_max = 2 * c->sm_count;
+    int wpr = 1;
+    while (wpr < 8 && M * wpr * 4 < (int64_t)blocks_max * 8 * 3 && ncg / (2 * wpr) >= 32) wpr *= 2;
+    const int64_t ctas_needed = (M * wpr + 7) / 8;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(blocks_max, ctas_needed));
+    const bool vreg = (ncg + wpr - 1) / wpr <= 32 * 8;
     if (group <= 0) { group = M; out_stride = 0; }
-    if (sq)
-        rowdot_kernel<T, true><<<blocks, 256, 0, c->stream>>>(Ablk, M, ncols, ld, vec, out, accumulate, group, out_stride);
-    else
-        rowdot_kernel<T, false><<<blocks, 256, 0, c->stream>>>(Ablk, M, ncols, ld, vec, out, accumulate, group, out_stride);
+#define RD_LAUNCH(SQ_, VR_)                                                                                         \
+    rowdot_kernel<T, SQ_, VR_><<<blocks, 256, 0, c->stream>>>(Ablk, M, ncols, ld, vec, out, accumulate, group, \
+                                                               out_stride, wpr)
+    if (sq) { if (vreg) RD_LAUNCH(true, true); else RD_LAUNCH(true, false); }
+    else    { if (vreg) RD_LAUNCH(false, true); else RD_LAUNCH(false, false); }
+#undef RD_LAUNCH
     CK(cudaGetLastError());
+    return 0;
+}
+
+// the TMA-streamed row dots (rowdot_stream) for matrices that fill the machine; *done stays false when the
+// shape is left to the load-batch kernel (small matrices, few rows, vec too long for shared memory)
+constexpr int64_t MS_MIN_BYTES = 4 << 20;
+constexpr int MS_TILE_TARGET = 24 << 10;
+template <typename T>
+static int rowdot_stream_try(b200l_ctx *c, const T *Ablk, int64_t M, int ncols, int64_t ld, const double *vec,
+                             double *out, int accumulate, bool *done) {
+    constexpr int V = VT<T>::V;
+    *done = false;
+    if (c->dbg & 262144) return 0;                               // (load-batch kernels only: tests, comparisons)
+    if ((int64_t)M * ncols * (int64_t)sizeof(T) < MS_MIN_BYTES || M < 2 * c->sm_count) return 0;
+    const int ncg = ncols / V;
+    MsParams p;
+    memset(&p, 0, sizeof(p));
+    p.A = Ablk; p.M = M; p.ld = ld; p.ncols = ncols; p.vec = vec; p.out = out; p.accumulate = accumulate;
+    p.SG = ncg <= 256 ? ncg : std::min(ncg, 1024);
+    p.ncs = (ncg + p.SG - 1) / p.SG;
+    const bool vreg = ncg <= 256;
+    const int vec_bytes = vreg ? 0 : (int)round_up((int64_t)ncols * 8, 128);
+    if (vec_bytes > 96 * 1024) return 0;
+    p.TR = std::max(1, std::min(MS_NW, MS_TILE_TARGET / (p.SG * 16)));
+    p.RC = (int)std::min<int64_t>(c->sm_count, M / p.TR);
+    if (p.RC < 1) return 0;
+    p.coop = (!vreg && p.TR == 1) ? 1 : 0;
+    p.contig = p.ncs == 1 && ld == ncols;
+    p.slot_bytes = (int)round_up((int64_t)p.TR * p.SG * 16, 128);
+    p.off_vec = 256;
+    p.off_part = p.off_vec + vec_bytes;
+    p.off_ring = (int)round_up(p.off_part + 2 * MS_NW * 8, 1024);
+    p.S = std::min(MS_MAXS, (c->smem_optin - p.off_ring) / p.slot_bytes);
+    if (p.S < 3) return 0;
+    const int smem = p.off_ring + p.S * p.slot_bytes;
+    const void *fn = vreg ? (const void *)rowdot_stream<T, true> : (const void *)rowdot_stream<T, false>;
+    const int fidx = vreg ? 1 : 2;
+    if (!(c->ms_ready & (1 << fidx))) {
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        c->ms_ready |= 1 << fidx;
+    }
+    void *args[] = {(void *)&p};
+    CK(cudaLaunchKernel(fn, dim3(p.RC), dim3(MS_THREADS), args, (size_t)smem, c->stream));
+    *done = true;
     return 0;
 }
 
@@ -2182,17 +2604,22 @@ template <typename T>
 static int gemv_t_dev(b200l_ctx *c, int m, const double *r, double *g) {
     const T *Ablk = reinterpret_cast<const T *>(c->A) + (int64_t)m * c->brows * c->ld;
     if (c->layout == B200L_ROWMAJOR)        // only the w real columns are written (g may hold exactly w entries)
-        return colwsum_dev<T>(c, Ablk, c->N, (int)c->ld, c->ld, r, g, false, 0, 1, 0, 0, c->w);
-    return rowdot_dev<T>(c, Ablk, c->w, (int)c->ld, c->ld, r, g, false, 0);
+        return colwsum_one<T>(c, Ablk, c->N, (int)c->ld, c->ld, r, g, 0, c->w);
+    bool done = false;
+    if (rowdot_stream_try<T>(c, Ablk, c->w, (int)c->ld, c->ld, r, g, 0, &done)) return 1;
+    return done ? 0 : rowdot_dev<T>(c, Ablk, c->w, (int)c->ld, c->ld, r, g, false, 0);
 }
 // q[N] (+)= A_m d[xld]
 template <typename T>
 static int gemv_n_dev(b200l_ctx *c, int m, const double *dvec, double *q, int accumulate) {
     const T *Ablk = reinterpret_cast<const T *>(c->A) + (int64_t)m * c->brows * c->ld;
-    if (c->layout == B200L_ROWMAJOR)
-        return rowdot_dev<T>(c, Ablk, c->N, (int)c->ld, c->ld, dvec, q, false, accumulate);
+    if (c->layout == B200L_ROWMAJOR) {
+        bool done = false;
+        if (rowdot_stream_try<T>(c, Ablk, c->N, (int)c->ld, c->ld, dvec, q, accumulate, &done)) return 1;
+        return done ? 0 : rowdot_dev<T>(c, Ablk, c->N, (int)c->ld, c->ld, dvec, q, false, accumulate);
+    }
     // (the pre-transposed block has ld >= N padded entries per column: only the N real ones are written)
-    return colwsum_dev<T>(c, Ablk, c->w, (int)c->ld, c->ld, dvec, q, false, accumulate, 1, 0, 0, (int)c->N);
+    return colwsum_one<T>(c, Ablk, c->w, (int)c->ld, c->ld, dvec, q, accumulate, (int)c->N);
 }
 
 static int need_A(b200l_ctx *c) {

@@ -159,7 +159,9 @@ int b200l_run_traced(b200l_ctx *ctx, int64_t nsteps, double mu, uint64_t *trace_
  * 5 s); when exceeded the kernel exits and b200l_run fails instead of hanging the device */
 int b200l_set_wait_limit(b200l_ctx *ctx, double seconds);
 /* diagnostics only: bit 0 skips the exchange waits, bit 1 the pass-1 arithmetic, bit 2 the
- * pass-2 arithmetic of the fused kernel, to time the remaining parts.  Results are invalid. */
+ * pass-2 arithmetic of the fused kernel, to time the remaining parts.  Results are invalid.
+ * Bit 18 (262144) is the one flag with valid results: the step-wise mat-vecs then always use the
+ * load-batch kernels instead of the TMA-streamed one (tests cover both). */
 int b200l_debug_flags(b200l_ctx *ctx, int32_t flags);
 
 /* -- synthetic instances on the device (reference recipe: parameters.py:20-28) ---------

@@ -33,14 +33,33 @@ def rel(a, b):
 # ---------------------------------------------------------------------------- kernels
 @pytest.mark.parametrize("TYPE", ["double", "float"])
 @pytest.mark.parametrize("LAYOUT", ["row", "transposed"])
-@pytest.mark.parametrize("shape", [(64, 256, 1), (257, 1002, 3), (1000, 4096, 2), (33, 35, 5), (5, 7, 7)])
+# (the two large shapes: several column slabs x many row chunks in the single-launch column sums, rows
+# shared by 2 and 8 warps in the row dots, vector kept in registers or not)
+@pytest.mark.parametrize("shape", [(64, 256, 1), (257, 1002, 3), (1000, 4096, 2), (33, 35, 5), (5, 7, 7),
+                                   (5000, 3000, 2), (300, 40000, 2), (2000, 12000, 2)])
 def test_matvec_kernels_vs_numpy(TYPE, LAYOUT, shape):
+    check_matvec_kernels(TYPE, LAYOUT, shape, 0)
+
+
+# the load-batch kernels (the fallback of the TMA-streamed mat-vec for small or very wide matrices) at shapes that
+# the streamed kernel would otherwise take
+@pytest.mark.parametrize("TYPE", ["double", "float"])
+@pytest.mark.parametrize("LAYOUT", ["row", "transposed"])
+@pytest.mark.parametrize("shape", [(1000, 4096, 2), (5000, 3000, 2), (300, 40000, 2)])
+def test_matvec_load_batch_kernels_vs_numpy(TYPE, LAYOUT, shape):
+    check_matvec_kernels(TYPE, LAYOUT, shape, 262144)
+
+
+def check_matvec_kernels(TYPE, LAYOUT, shape, dbg):
     N, K, BLOCK = shape
     rng = np.random.RandomState(N + K)
     A = rng.randn(N, K)
     if TYPE == "float":
         A = A.astype(np.float32).astype(np.float64)      # same matrix on both sides
     cal = make_gpu_cal(A, BLOCK, TYPE, LAYOUT)
+    if dbg:
+        from convex_optimization_b200 import _lib
+        _lib.check(cal._lib.b200l_debug_flags(cal.ctx, dbg))
     w = K // BLOCK
     assert cal.MAT_HEIGHT == N and cal.MAT_WIDTH == w and cal.MAT_WIDTH_ALL == K
     assert tuple(cal.A_b_gpu[0].shape) == (N, w)

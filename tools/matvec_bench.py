@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--layout", default="row", choices=["row", "transposed"])
     ap.add_argument("--dtype", default="float", choices=["float", "double"])
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--dbg", type=int, default=0, help="b200l_debug_flags (262144: load-batch kernels only)")
     args = ap.parse_args()
     cfg = CONFIGS["c2"]
     N, K, BLOCK = cfg["N"], cfg["K"], cfg["BLOCK"]
@@ -39,6 +40,8 @@ def main():
     tdt = torch.float32 if args.dtype == "float" else torch.float64
     store, b, mu = make_device_instance(torch, dev, N, K, BLOCK, 0.01, 2, tdt, ld, args.layout)
     cal = Cal.from_device_blocks(store, N, K, BLOCK)
+    if args.dbg:
+        _lib.check(cal._lib.b200l_debug_flags(cal.ctx, args.dbg))
     stream = torch.cuda.current_stream(dev)
     _lib.check(cal._lib.b200l_ctx_set_stream(cal.ctx, ctypes.c_void_p(stream.cuda_stream)))
     r = torch.randn(max(N, cal.ld) + 64, dtype=torch.float64, device=dev)
