@@ -705,8 +705,10 @@ def main_gpu(args):
     cx.barrier()
     t0 = time.time()
     e2e_steps = max(3, min(args.steps, 10))
+    e2e_kernel_ms = 0.0
     for _ in range(e2e_steps):
         solver.run(SILENCE=True)
+        e2e_kernel_ms += solver.kernel_ms
     cx.barrier()
     e2e_dt = cx.max_over_ranks(time.time() - t0)
     e2e_value = world * e2e_steps * e2e_sweeps / e2e_dt
@@ -754,9 +756,10 @@ def main_gpu(args):
                        "launch": geo, "objective_after_bench": obj_bench},
             "roofline": roof,
             "e2e": {"value": e2e_value, "unit": UNIT,
-                    "h2d_bytes_per_step": int(N * 8 + 4 * BLOCK * e2e_sweeps),
+                    "h2d_bytes_per_step": int(N * 8),
                     "d2h_bytes_per_step": int(K * 8 + 24),
                     "sweeps_per_call": e2e_sweeps, "calls": e2e_steps, "nnz_x": nnz,
+                    "wall_ms_per_call": e2e_dt * 1e3 / e2e_steps, "kernel_ms_per_call": e2e_kernel_ms / e2e_steps,
                     "api": "ClassLasso.run() (host b -> device, fused solve, x -> host)"},
             "gpu_launches": n_launches,
             "clocks": clocks,
@@ -811,7 +814,8 @@ def main():
     ap.add_argument("--quick", action="store_true", help="headline leg only (no sub-records of the other configurations)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle-checked solve in front of the timing")
-    ap.add_argument("--e2e-sweeps", type=int, default=5)
+    ap.add_argument("--e2e-sweeps", type=int, default=10,
+                    help="sweeps per ClassLasso.run() call of the e2e leg (a C2 solve to eps = 1e-4 takes 9)")
     ap.add_argument("--instance", default="torch", choices=["torch", "philox"],
                     help="how the synthetic instance is generated on the device: torch RNG per rank (default) or "
                          "b200l_gen_gaussian (Philox keyed by seed/row/global column)")

@@ -231,9 +231,12 @@ class ClassLasso(ClassLassoCPU):
                              % (tuple(self.A_SHAPE), self.BLOCK, self.gpu_cal.MAT_HEIGHT, K,
                                 self.gpu_cal.Block))
         bounded = isinstance(ERR_BOUND, float)
-        order = np.fromiter((self.index_get(t) for t in range(self.ITER_MAX)),
-                            dtype=np.int32, count=self.ITER_MAX)
-        order = self._shared_order(order)
+        if type(self).index_get is ClassLassoCPU.index_get:
+            order = None         # the cyclic order t % BLOCK (ref lasso.py:40-41) is the kernel's own
+        else:
+            order = np.fromiter((self.index_get(t) for t in range(self.ITER_MAX)),
+                                dtype=np.int32, count=self.ITER_MAX)
+            order = self._shared_order(order)
         if self._custom_diag:
             self.gpu_cal._use_custom_diag(self.d_ATA)
         else:
@@ -252,7 +255,7 @@ class ClassLasso(ClassLassoCPU):
         _lib.check(lib.b200l_set_problem(ctx, _lib.dptr(b)))            # H2D b, x = 0, r = -b
         t_launch = time.time() - start
         _lib.check(lib.b200l_run(
-            ctx, order.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), self.ITER_MAX,
+            ctx, order.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)) if order is not None else None, self.ITER_MAX,
             float(self.mu), float(ERR_BOUND) if bounded else -1.0,
             _lib.dptr(errs) if errs is not None else None,
             _lib.dptr(times) if times is not None else None,
