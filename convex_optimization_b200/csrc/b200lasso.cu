@@ -353,7 +353,11 @@ struct RunParams {
     int32_t gate_mode;        // 0: re-stream freely, 1/2/3: after inbox fetch issued / gather done / D fetch issued
     // transposed layout: a tile is TJ block columns x BX residual entries of this CTA
     // (BX/V odd: conflict-free 16-byte reads with lanes on consecutive columns)
+    // A CTA's BX entries come as NBX boxes of BXb = BXVb * V entries each (TMA boxes hold at most 256 elements per
+    // dimension); P1 threads share a column in pass 1 (TJ * P1 = consumer threads), BXVb = P1 * odd keeps their
+    // 16-byte reads conflict-free.
     int32_t BX, BXV, TJ, nparts, nt_t, off_red2;
+    int32_t NBX, BXb, BXVb, P1;
     int32_t mw, mw_shift, nown;     // message words (a power of two), owner CTAs
     int32_t dpw, dsec, ackbase;     // step D: columns per 16-byte word, published by whole sectors, first acknowledgement word
     // shared-memory offsets
@@ -504,6 +508,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
     constexpr int WPC = LL::WPC;
     constexpr int DK = CPT == 1 ? NTC / 32 : 0;
     constexpr bool MG = MODE >= 1, DIAG = MODE == 2;
+    // pre-transposed layout: CPT selects the tile shape -- 1: one thread and one TMA box per column (N / #SM <= 252
+    // entries, C2), 2: the general shape (P1 threads per column, NBX boxes); a runtime switch cost 2.7 % on C2
+    constexpr bool TGEN = TRANS && CPT > 1;
     const int WORLD = MG ? p.world : 1, DBG = DIAG ? p.dbg : 0;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *ring = smem;
@@ -621,9 +628,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                         if (!live) break;
                         if (TRANS) {
                             mbar_expect_tx(full + cur.slot, (uint32_t)(p.TJ * p.BX) * (uint32_t)sizeof(T));
-                            tma_load_2d(ring + (size_t)cur.slot * p.slot_bytes, &tmap, (int)row0, ym + t * p.TJ,
-                                        full + cur.slot);
-                            if (pass == 1 && An) tma_prefetch_2d(&tmap, (int)row0, yn + t * p.TJ);
+                            for (int bx = 0; bx < (TGEN ? p.NBX : 1); ++bx) {
+                                tma_load_2d(ring + (size_t)cur.slot * p.slot_bytes + (size_t)bx * p.TJ * p.BXb * sizeof(T),
+                                            &tmap, (int)row0 + bx * p.BXb, ym + t * p.TJ, full + cur.slot);
+                                if (pass == 1 && An) tma_prefetch_2d(&tmap, (int)row0 + bx * p.BXb, yn + t * p.TJ);
+                            }
                         } else {
                             const uint32_t bytes = t == nt - 1 ? last_bytes : tile_bytes;
                             mbar_expect_tx(full + cur.slot, bytes);
@@ -1029,25 +1038,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                     const T *rTt = rT + t * TR, *qTt = qT + t * TR;
                     if (WORLD > 1 && have_prev) wait_q(step_prev, TRANS ? rows_c : t * TR + rows_t);
                     if (TRANS) {
-                        // thread = block column t*TJ + tid: dot products of its BX entries with r and q,
-                        // complete for this CTA's rows, published at once (one tagged word per column)
-                        const int j = t * p.TJ + tid;
+                        // P1 threads (adjacent lanes) per block column t*TJ + jl: dot products of the column's BX
+                        // entries with r and q, complete for this CTA's rows, published at once (one tagged
+                        // word per column)
+                        const int P1 = TGEN ? p.P1 : 1;
+                        const int part = tid & (P1 - 1), jl = tid / P1;
+                        const int j = t * p.TJ + jl;
                         Acc a0, a1;
                         OP::zero(a0);
                         OP::zero(a1);
-                        if (tid < p.TJ && j < p.w && !(DBG & 2)) {
-                            const T *col = tile + (size_t)tid * p.BX;
+                        if (j < p.w && !(DBG & 2)) {
+                            if (!TGEN) {                          // one thread, one box per column (C2)
+                                const T *col = tile + (size_t)tid * p.BX;
 #pragma unroll 4
-                            for (int iv = 0; iv < p.BXV; ++iv) {
-                                const VecT v = *reinterpret_cast<const VecT *>(col + iv * V);
-                                OP::mac(a0, v, *reinterpret_cast<const VecT *>(rT + iv * V));
-                                OP::mac(a1, v, *reinterpret_cast<const VecT *>(qT + iv * V));
+                                for (int iv = 0; iv < p.BXV; ++iv) {
+                                    const VecT v = *reinterpret_cast<const VecT *>(col + iv * V);
+                                    OP::mac(a0, v, *reinterpret_cast<const VecT *>(rT + iv * V));
+                                    OP::mac(a1, v, *reinterpret_cast<const VecT *>(qT + iv * V));
+                                }
+                            } else {
+                                for (int bx = 0; bx < p.NBX; ++bx) {
+                                    const T *col = tile + ((size_t)bx * p.TJ + jl) * p.BXb;
+                                    const T *rb = rT + bx * p.BXb, *qb = qT + bx * p.BXb;
+#pragma unroll 4
+                                    for (int iv = part; iv < p.BXVb; iv += P1) {
+                                        const VecT v = *reinterpret_cast<const VecT *>(col + iv * V);
+                                        OP::mac(a0, v, *reinterpret_cast<const VecT *>(rb + iv * V));
+                                        OP::mac(a1, v, *reinterpret_cast<const VecT *>(qb + iv * V));
+                                    }
+                                }
                             }
                         }
-                        if (tid < p.TJ && j < G * cs) {
+                        T sr = OP::hsum(a0), sq = OP::hsum(a1);
+                        if (TGEN) {
+#pragma unroll
+                            for (int o = 1; o < 8; o <<= 1) {
+                                if (o < P1) {
+                                    sr += __shfl_xor_sync(0xffffffffu, sr, o);
+                                    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                                }
+                            }
+                        }
+                        if (part == 0 && j < G * cs) {
                             const int rd = j >> p.cs_shift;
                             const int jj = j & (cs - 1);
-                            LL::put(p.gLL + ((size_t)rd * G + c) * p.mw + jj * WPC, OP::hsum(a0), OP::hsum(a1), tag);
+                            LL::put(p.gLL + ((size_t)rd * G + c) * p.mw + jj * WPC, sr, sq, tag);
                         }
                     } else if (p1_active && !(DBG & 2)) {
                         if (TR >= 4) {
@@ -1453,6 +1488,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
             Acc accT;                      // TRANS: this thread's residual entries, all columns
             OP::zero(accT);
             const int ivT = TRANS ? tid % p.BXV : 0, partT = TRANS ? tid / p.BXV : 0;
+            // (my group inside its box: box ivT / BXVb, all TJ columns of a box are adjacent in the slot)
+            const size_t offT = TGEN ? (size_t)(ivT / p.BXVb) * p.TJ * p.BXb + (size_t)(ivT % p.BXVb) * V : (size_t)ivT * V;
+            const int strideT = TGEN ? p.BXb : p.BX;
             {
                 // Rows of the tile against D.  Narrow blocks (D in registers): all loads of a row pair
                 // go out as one batch (NK per row: the smallest of 2 / 4 / 8 that covers the block; a
@@ -1538,7 +1576,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                         if (partT < p.nparts && !(DBG & 4)) {
 #pragma unroll 4
                             for (int j = partT; j < cols_t; j += p.nparts) {
-                                const VecT v = *reinterpret_cast<const VecT *>(tile + (size_t)j * p.BX + ivT * V);
+                                const VecT v = *reinterpret_cast<const VecT *>(tile + offT + (size_t)j * strideT);
                                 OP::axpy(accT, v, delta_s[t * p.TJ + j]);
                             }
                         }
@@ -2932,7 +2970,7 @@ typedef void (*fused_fn)(const RunParams, const CUtensorMap);
 
 template <typename T, int MODE>
 static fused_fn pick_kernel(int cpt, bool trans) {
-    if (trans) return lasso_fused<T, 1, true, MODE>;
+    if (trans) return cpt == 1 ? lasso_fused<T, 1, true, MODE> : lasso_fused<T, 2, true, MODE>;
     switch (cpt) {
         case 1: return lasso_fused<T, 1, false, MODE>;
         case 2: return lasso_fused<T, 2, false, MODE>;
@@ -2968,7 +3006,7 @@ static int make_tensor_map(b200l_ctx *c) {
     }
     const cuuint64_t dims[2] = {(cuuint64_t)c->ld, (cuuint64_t)c->nblocks * (cuuint64_t)c->brows};
     const cuuint64_t strides[1] = {(cuuint64_t)c->ld * c->esize};
-    const cuuint32_t box[2] = {(cuuint32_t)c->geo.BX, (cuuint32_t)c->geo.TJ};
+    const cuuint32_t box[2] = {(cuuint32_t)c->geo.BXb, (cuuint32_t)c->geo.TJ};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = encode(&c->tmap, c->dtype == B200L_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
                               2, const_cast<void *>(c->A), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -3007,25 +3045,18 @@ static int plan_geometry(b200l_ctx *c) {
     int TR = (int)std::min<int64_t>(64, std::max<int64_t>(1, slot_target / rowbytes));
     TR = std::min(TR, (int)round_up(std::max(rows_max, 1), 4));
     if (TR >= 4) TR &= ~3;
-    // transposed layout: box of BX residual entries (odd number of 16-byte groups) x TJ columns
-    const int BXV = ((rows_max + V - 1) / V) | 1;
-    const int BX = BXV * V;
-    // (columns per tile: one per thread in pass 1; fewer when a CTA's share of a column is long, so that
-    // at least three tiles fit the ring -- fp64 with N / #SM = 68 entries: 256 columns would be 143 KB)
-    int TJ = NTC;
-    while (trans && TJ > 32 && (int64_t)TJ * BX * es > 70000) TJ >>= 1;   // (fp32 C2: 256 x 68 x 4 = 69632, three slots)
-    const int nt_t = (c->w + TJ - 1) / TJ;
-    const int nparts = std::max(1, std::min(NTC / BXV, 32));
-    if (trans && BX > 256)
-        return fail("transposed layout: N/#SM = %d residual entries per CTA exceed the 256-element TMA box; use "
-                    "the row-major layout for N > %d", rows_max, 252 * G);
+    // transposed layout: a tile is TJ columns x BX residual entries, fetched as NBX boxes of BXb = BXVb * V entries
+    // (at most 256 elements per box dimension).  P1 = NTC / TJ threads share a column in pass 1; BXVb = P1 * odd
+    // keeps the 16-byte reads of a quarter-warp (8 / P1 columns x P1 parts) on distinct banks.  The values are
+    // chosen below, once the fixed part of the shared memory is known.
+    int BXV = 1, BX = V, TJ = NTC, nt_t = 1, nparts = 1, NBX = 1, BXVb = 1, P1 = 1;
     // columns of every block owned by one CTA: a power of two (shift/mask addressing)
     int cs = 1, cs_shift = 0;
     while (cs * G < ld) { cs *= 2; ++cs_shift; }
     if (cs > MAX_CS) return fail("internal: slice width %d > %d", cs, MAX_CS);
     const int direct_pre = (!trans && nrg == 1 && cs * (es / 4) >= 4 && !(c->dbg & 128)) ? 1 : 0;
-    const int slot_bytes = trans ? (int)round_up((int64_t)TJ * BX * es, 128) : (int)round_up((int64_t)TR * rowbytes, 128);
-    const int rows_pad = trans ? (int)round_up(BX, 8) : (int)round_up(std::max(rows_max, 1), std::max(TR, 8));
+    int slot_bytes = trans ? 0 : (int)round_up((int64_t)TR * rowbytes, 128);
+    int rows_pad = trans ? 0 : (int)round_up(std::max(rows_max, 1), std::max(TR, 8));
 
     int off = 0;
     auto take = [&](int bytes) { int o = off; off += (int)round_up(bytes, 128); return o; };
@@ -3062,6 +3093,49 @@ static int plan_geometry(b200l_ctx *c) {
             out->tile_sends = (c->world > 1 && !trans && nt_plan <= 128 && !(c->dbg & 256) && !one_store) ? 1 : 0;
         }
     };
+    if (trans) {
+        // columns per tile: one per thread in pass 1 when a CTA's share of a column is short; longer shares halve
+        // TJ (P1 = 2, 4, 8 threads per column) until the ring holds at least two tiles.  Among the feasible
+        // shapes the one that fetches the fewest padding entries wins, then the one with three or more slots,
+        // then the widest tile.  (fp32 C2: 256 x 68, three slots; fp64 C2: 128 x 68; fp32 C4 shard: 64 x 352 in
+        // two boxes of 176.)
+        const int need = (rows_max + V - 1) / V;             // 16-byte groups of residual entries per CTA
+        const int maxb = 256 / V;                            // groups per box
+        double best = 1e30;
+        int bP1 = 0, bNBX = 0, bBXVb = 0;
+        for (int p1 = 1; p1 <= 8; p1 *= 2) {
+            const int nb0 = (need + maxb - 1) / maxb;
+            for (int nb = nb0; nb <= nb0 + 2; ++nb) {
+                int k = ((need + nb - 1) / nb + p1 - 1) / p1;
+                if (!(k & 1)) ++k;
+                const int bxvb = p1 * k;
+                if (bxvb > maxb || nb * bxvb > NTC) continue;
+                BXV = nb * bxvb; BX = BXV * V; TJ = NTC / p1;
+                nt_t = (c->w + TJ - 1) / TJ;
+                nparts = std::max(1, std::min(NTC / BXV, 32));
+                rows_pad = (int)round_up(BX, 8);
+                slot_bytes = (int)round_up((int64_t)TJ * BX * es, 128);
+                if (c->slot_target > 0 && slot_bytes > c->slot_target && p1 < 8) continue;   // (b200l_set_tuning)
+                off = 0;
+                fixed_part(nullptr);
+                const int slots = (c->smem_optin - off) / slot_bytes;
+                if (slots < 2) continue;
+                const double cost = (double)BXV / need * (slots >= 3 ? 1.0 : 1.03) * (1.0 + 1e-3 * (nb - nb0)) *
+                                    (1.0 + 1e-4 * p1);
+                if (cost < best) { best = cost; bP1 = p1; bNBX = nb; bBXVb = bxvb; }
+            }
+        }
+        if (!bP1)
+            return fail("transposed layout: N/#SM = %d residual entries per CTA do not fit the fused kernel "
+                        "(at most %d); use the row-major layout", rows_max, NTC * V);
+        P1 = bP1; NBX = bNBX; BXVb = bBXVb;
+        cpt = (P1 == 1 && NBX == 1) ? 1 : 2;              // (selects the kernel instantiation, see TGEN)
+        BXV = NBX * BXVb; BX = BXV * V; TJ = NTC / P1;
+        nt_t = (c->w + TJ - 1) / TJ;
+        nparts = std::max(1, std::min(NTC / BXV, 32));
+        rows_pad = (int)round_up(BX, 8);
+        slot_bytes = (int)round_up((int64_t)TJ * BX * es, 128);
+    }
     // the ring goes first (offset 0); sized after the fixed part is known
     off = 0;
     fixed_part(nullptr);
@@ -3102,6 +3176,7 @@ static int plan_geometry(b200l_ctx *c) {
     g.dsec = cs >= 2 * g.dpw ? 1 : 0;
     g.ackbase = (int)round_up(ld / g.dpw, 2);
     g.BX = BX; g.BXV = BXV; g.TJ = TJ; g.nparts = nparts; g.nt_t = nt_t;
+    g.NBX = NBX; g.BXb = BXVb * V; g.BXVb = BXVb; g.P1 = P1;
     c->tmap_valid = 0;
     g.inflight = c->max_inflight > 0 ? std::min(c->max_inflight, S) : S;
     // HBM one block ahead through L2 only pays when this block (re-read by pass 2) and the next

@@ -211,7 +211,7 @@ class ClassLasso(ClassLassoCPU):
 
     def _fused_supported(self):
         """the fused kernel has shape limits the reference does not (a row of a block must fit a
-        32 KiB tile, N / #SM <= 252 for the pre-transposed layout); shapes beyond them run the
+        32 KiB tile, N / #SM <= 1024 fp32 / 512 fp64 entries for the pre-transposed layout); shapes beyond them run the
         step-wise path on the library's mat-vec kernels instead, with a warning"""
         try:
             self.gpu_cal.run_config()

@@ -341,9 +341,11 @@ def test_traces_written_for_compare_py(tmp_path):
 
 @pytest.mark.parametrize("TYPE", ["double", "float"])
 @pytest.mark.parametrize("shape", [(300, 2400, 4, 0.05), (257, 1002, 3, 0.05), (1000, 4000, 2, 0.02),
-                                   (33, 70, 5, 0.2), (2000, 3000, 1, 0.02)])
+                                   (33, 70, 5, 0.2), (2000, 3000, 1, 0.02),
+                                   (20000, 600, 2, 0.02), (40000, 768, 2, 0.02)])
 def test_fused_transposed_layout_vs_oracle(shape, TYPE):
-    """the pre-transposed (BLOCK, w, N) layout through the fused kernel (2-D TMA boxes)"""
+    """the pre-transposed (BLOCK, w, N) layout through the fused kernel (2-D TMA boxes); the two tall shapes:
+    2, 4 or 8 threads per column in pass 1, and a CTA's share of a column fetched as two boxes"""
     from convex_optimization_b200 import lasso
     N, K, BLOCK, den = shape
     A, _, b, mu = orc.make_problem(N, K, den, seed=N + K + 1)
