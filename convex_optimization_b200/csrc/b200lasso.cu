@@ -66,7 +66,10 @@ constexpr int NTC = NW * 32;           // consumer threads
 // (setmaxnreg), whose inner loops want many loads in flight.
 constexpr int NTHREADS = NTC + 128;
 constexpr int HELPER_REGS = 56, CONSUMER_REGS = 224;            // 256 * 224 + 128 * 56 = 64512 = 384 * 168
-constexpr int HELPER_REGS_MG = 152, CONSUMER_REGS_MG = 176;    // (the collector warp keeps up to 21 words per lane in flight)
+// (the collector warp keeps up to 21 words per lane in flight.  Measured with other splits, 2 GPUs, C2 shards:
+// consumers 192 / helpers 120: 1037 shard sweeps/s, 208 / 88: 899, 224 / 56: 771 against 1202 -- the spills of the
+// helper warps sit on the critical path of every step)
+constexpr int HELPER_REGS_MG = 152, CONSUMER_REGS_MG = 176;
 constexpr int MAX_CS = 64;             // max stage-2 slice width (columns per CTA)
 
 template <typename T> struct VT;

@@ -30,8 +30,13 @@ def main():
     cases = [(300, 2400, 4, 0.05, "double", 7, "row"), (257, 1024 * world, 8, 0.03, "double", 11, "row"),
              (1000, 8000, 2, 0.02, "float", 5, "row"), (64, 64 * world, 1, 0.2, "double", 3, "row"),
              (12000, 64 * world, 2, 0.1, "double", 13, "row"), (600, 1600, 2, 0.05, "double", 17, "transposed"),
-             (1200, 2400, 3, 0.04, "float", 19, "transposed")]
-    for (N, K, BLOCK, den, TYPE, seed, LAYOUT) in cases:
+             (1200, 2400, 3, 0.04, "float", 19, "transposed"),
+             # tall: the general pre-transposed tile shape (four threads per column in pass 1).  Tall, narrow
+             # instances are sensitive to the summation order -- the oracle's own runs with P = 1 and P = world
+             # differ by 1e-10 .. 1.4e-9 on them (seeds 23 .. 47) -- hence the wider tolerance of this case
+             (24000, 128 * world, 2, 0.1, "double", 29, "transposed", 2e-8)]
+    for case in cases:
+        (N, K, BLOCK, den, TYPE, seed, LAYOUT), case_tol = case[:7], (case[7] if len(case) > 7 else None)
         A, _, b, mu = orc.make_problem(N, K, den, seed=seed)
         if TYPE == "float":
             A = A.astype(np.float32).astype(np.float64)
@@ -53,7 +58,7 @@ def main():
         err_iter = np.zeros(ITER_MAX)
         solver.run(bound, err_iter=err_iter, SILENCE=True)
         x = dd.gather_x(solver.x, BLOCK)
-        tol = 1e-10 if TYPE == "double" else 1e-5
+        tol = case_tol if case_tol is not None else (1e-10 if TYPE == "double" else 1e-5)
         rel = np.abs(x - o["x"]).max() / np.abs(o["x"]).max()
         same_iters = solver.iters == o["iters"]
         try:                                   # fp64: identical patterns; fp32: the rule of conftest.assert_support
