@@ -788,6 +788,11 @@ def main_gpu(args):
         # global matrix for every world size
         others["c4_shard_per_gpu"] = leg(cx, "c4shard", CONFIGS["c4shard"], "row", "philox", nsw, 2,
                                          ("c4shard", "row"), l2_bytes, standalone_first=True)
+        if world == 1:
+            # the same shard pre-transposed: N / #SM = 338 entries per CTA, i.e. two TMA boxes per tile and four
+            # threads per column in pass 1 (the general tile shape of the pre-transposed layout)
+            others["c4_shard_transposed"] = leg(cx, "c4shard", CONFIGS["c4shard"], "transposed", "philox", nsw, 2,
+                                                ("c4shard", "transposed"), l2_bytes)
     if rank == 0:
         if others:
             line["configs"] = others
