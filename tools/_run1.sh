@@ -1,11 +1,9 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r2z_pytest.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/r2z_pytest.log
-timeout 300 python __graft_entry__.py smoke > gpurun_out/r2z_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/r2z_smoke.log
-timeout 900 python bench.py > gpurun_out/r2z_bench.log 2> gpurun_out/r2z_bench.err; echo "bench rc=$?"; tail -1 gpurun_out/r2z_bench.log | python -c "
-import sys,json
-d=json.loads(sys.stdin.read())
-print('value',d['value'],'e2e', d['e2e']['value'], 'frac', d['roofline']['frac'], 'tte', d['time_to_eps']['ms'], d['time_to_eps']['e2e_ms'])
-for k,v in d['configs'].items(): print(k, v.get('value'), v.get('ms_per_sweep'), v['roofline']['frac'])
-print(d['cpu_baseline']['value'], d['cpu_baseline']['kind'])
-"
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2z_refarm.log 2>&1; echo "ref arm rc=$?"; tail -1 gpurun_out/r2z_refarm.log | cut -c1-400
+for sb in 0 32768 40960 57344 65536; do for inf in 0 3; do
+v=$(timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu --eps 0 --quick --no-parity --e2e-sweeps 1 --slot-bytes $sb --inflight $inf 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value'],1), d['config']['launch']['tile_rows'], d['config']['launch']['ring_slots'])")
+echo "slot=$sb inflight=$inf: $v"
+done; done
+for d in 32 64 96; do
+v=$(timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu --eps 0 --quick --no-parity --e2e-sweeps 1 --dbg $d 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value'],1))")
+echo "gate dbg=$d: $v"
+done
