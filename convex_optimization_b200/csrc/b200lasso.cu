@@ -308,6 +308,7 @@ struct Ctl {
     int stop;
     int abort;
     long long gate;                  // steps whose pass-2 copies the producer may issue
+    long long gate2;                 // steps whose step-D gather is complete (pass-2 tiles past the first gate2_tiles)
     long long sc_go, sc_done;        // steps whose scalars are final in sp / whose totals are in tot (scalar warp)
     double tot[4];                   // line-search scalars of the pending step summed over all CTAs
     long long qready;                // multi-GPU: (step + 1) << 32 | rows of A_m D summed over the ranks
@@ -354,6 +355,7 @@ struct RunParams {
     ulonglong2 *mc;           // multicast mapping of all ranks' inboxes (NVLS) or NULL
     int32_t direct_pub;       // partial gradients are published from registers (one row group)
     int32_t gate_mode;        // 0: re-stream freely, 1/2/3: after inbox fetch issued / gather done / D fetch issued
+    int32_t gate2_tiles;      // > 0: only this many pass-2 tiles are staged before the step-D gather is complete
     // transposed layout: a tile is TJ block columns x BX residual entries of this CTA
     // (BX/V odd: conflict-free 16-byte reads with lanes on consecutive columns)
     // A CTA's BX entries come as NBX boxes of BXb = BXVb * V entries each (TMA boxes hold at most 256 elements per
@@ -560,6 +562,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
         ctl->stop = 0;
         ctl->abort = 0;
         ctl->gate = 0;
+        ctl->gate2 = 0;
         ctl->sc_go = 0;
         ctl->sc_done = 0;
         ctl->qready = 0;
@@ -614,6 +617,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                         if (!live) break;
                     }
                     for (int t = 0; t < nt; ++t) {
+                        if (pass == 1 && p.gate2_tiles && t >= p.gate2_tiles) {
+                            while (*(volatile long long *)&ctl->gate2 <= step) {
+                                if (*stopf) { live = false; break; }
+                            }
+                            if (!live) break;
+                        }
                         // pacing: a bounded number of bulk copies in flight
                         while (k - kd >= max_inflight) {
                             if (mbar_try_wait(full + dcur.slot, dcur.phase)) {
@@ -1430,6 +1439,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lasso_fused(const RunParams p, co
                 }
             }
             cbar();
+            if (tid == 0 && p.gate2_tiles) *(volatile long long *)&ctl->gate2 = step + 1;
             if (trace && !drain) trace[step * NTRACE + 7] = tstamp() - c_start;
             if (*(volatile int *)&ctl->abort) {
                 aborted = 1;
@@ -3193,6 +3203,12 @@ static int plan_geometry(b200l_ctx *c) {
     // (diagnostics: dbg bits 5-6 = 1 / 2 / 3 select modes 0 / 1 / 3)
     const int gm = (c->dbg >> 5) & 3;
     g.gate_mode = gm == 0 ? 2 : (gm == 1 ? 0 : (gm == 2 ? 1 : 3));
+    // ... and the last ring slot is only filled once the step-D gather is complete: with all four slots in flight
+    // the gather's polls queue behind one more tile on the L2 link (measured on C2, one GPU, same box: 832.5 vs
+    // 822.5 sweeps/s; holding back two slots 812, three 760).  Blocks that stay in L2, one GPU, row-major, at
+    // least four slots; dbg bits 20-22 = 1..6 set the number of early tiles, 7 switches the second gate off.
+    const int g2 = (c->dbg >> 20) & 7;
+    g.gate2_tiles = g2 == 7 ? 0 : (g2 ? g2 : ((l2_resident && !trans && c->world == 1 && S >= 4) ? S - 1 : 0));
 
     // inboxes of the partial block gradients: [G readers][G writers][cs][WPC] LL words
     const size_t need = (size_t)G * G * mw * 16;
