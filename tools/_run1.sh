@@ -1,8 +1,10 @@
-export B200L_LIB=$PWD/_ab_old/libb200lasso_head.so
-r=$(timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu --eps 0 --quick --no-parity --e2e-sweeps 1 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value'],1), d['ms_per_step'])")
-echo "head: $r"
-unset B200L_LIB
-for d in 0 16777216 25165824 8388608 0 16777216; do
-r=$(timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu --eps 0 --quick --no-parity --e2e-sweeps 1 --dbg $d 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value'],1), d['ms_per_step'])")
-echo "new dbg=$d: $r"
+# one-GPU validation on a B200 box (gpurun -- 'bash tools/_run1.sh'): GPU tests, smoke, the default bench line,
+# the step-wise mat-vec roofline; logs under gpurun_out/
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/val_pytest.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/val_pytest.log
+timeout 300 python __graft_entry__.py smoke > gpurun_out/val_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/val_smoke.log
+timeout 900 python bench.py > gpurun_out/val_bench.log 2> gpurun_out/val_bench.err; echo "bench rc=$?"; tail -1 gpurun_out/val_bench.log | cut -c1-400
+for a in "" "--layout transposed" "--dtype double"; do
+n=$(echo $a | tr -d ' -')
+timeout 200 python tools/matvec_bench.py $a > gpurun_out/val_matvec_$n.log 2>&1; tail -1 gpurun_out/val_matvec_$n.log | cut -c1-600
 done
