@@ -52,10 +52,12 @@ def main():
     out = {"config": "C2 blocks: %s %dx%d per block, %s layout, 100 blocks cycled (HBM-resident)" % (args.dtype, N, w, args.layout),
            "peak_GBs": peak, "peak_source": src, "block_bytes": N * w * es}
 
-    def timed(fn, ptr_in, ptr_out):
+    def timed(fn, ptr_in, ptr_out, fn2=None, ptr_in2=None, ptr_out2=None):
         def sweep():
             for m in range(BLOCK):
                 _lib.check(fn(cal.ctx, m, ctypes.c_void_p(ptr_in), ctypes.c_void_p(ptr_out)))
+                if fn2 is not None:         # the step-wise solver's pattern: A_m^T r, then A_m d, per block
+                    _lib.check(fn2(cal.ctx, m, ctypes.c_void_p(ptr_in2), ctypes.c_void_p(ptr_out2)))
         sweep()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -94,6 +96,10 @@ def main():
         return rec
     out["gemv_t (A_m^T r)"] = timed(cal._lib.b200l_gemv_t_dev, r.data_ptr(), g.data_ptr())
     out["gemv_n (A_m d)"] = timed(cal._lib.b200l_gemv_n_dev, d.data_ptr(), q.data_ptr())
+    # both mat-vecs per block, alternating like the step-wise solver (the second one finds the block in L2):
+    # us_per_call here is per PAIR of calls
+    out["gemv_t + gemv_n per block, alternating (us per pair)"] = timed(
+        cal._lib.b200l_gemv_t_dev, r.data_ptr(), g.data_ptr(), cal._lib.b200l_gemv_n_dev, d.data_ptr(), q.data_ptr())
     # diag(A^T A): one pass over the whole matrix (re-bind to invalidate the cached diagonal)
     dh = np.empty((BLOCK, w, 1))
     ts = []
