@@ -15,7 +15,8 @@ between timed steps.
 `value`  : sweeps/s with everything resident in HBM (K fused launches, CUDA events).
 `e2e`    : sweeps/s through the reference-facing API, ClassLasso.run(): host b -> device,
            the solve, x -> host, all inside the timed region (A is uploaded once by
-           GPU_Calculation(A, BLOCK), exactly as in the reference driver cpu_vs_gpu.py:131).
+           GPU_Calculation(A, BLOCK), exactly as in the reference driver cpu_vs_gpu.py:131);
+           10 sweeps per call by default -- a solve of C2 to eps = 1e-4 takes 9.
 `roofline`: algorithmic bytes of a sweep / kernel time vs the
            measured HBM copy peak of MEASURED_PEAKS.json.
 `cpu_baseline`: the reference's own ClassLassoCPU.run (oracle/_ref, an unmodified copy made by
