@@ -58,6 +58,12 @@ def make(src=None, verbose=False):
             print("copied %s -> %s" % (s, d))
     with open(os.path.join(DEST, MANIFEST), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
+    with open(os.path.join(DEST, "README.txt"), "w") as f:
+        f.write("Byte-identical copies of the reference's own files (see MANIFEST.json), made by oracle/make_ref.py\n"
+                "from %s.  NOT this repository's code and not tracked by git (.gitignore: oracle/_ref/):\n"
+                "the directory exists so that bench.py --impl reference can time the UNMODIFIED ClassLassoCPU on\n"
+                "the GPU box (VERDICT round 1, \"Make the CPU arm the reference\") and so that the drop-in tests\n"
+                "can run the unmodified drivers.  Nothing under convex_optimization_b200/ imports it.\n" % src)
     return DEST
 
 
